@@ -1,0 +1,170 @@
+/* jpezy_b200.h -- C ABI of the B200-native baseline-JPEG hot path behind falgon/jpezy's
+ * encoder / decoder classes.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * tree).  Plain pointers and sizes only; no C++/torch types.  Pointers named d_* are device
+ * pointers on the context's device, `stream` is a cudaStream_t passed as void* (NULL = the
+ * context's own stream).  Host-pointer entry points synchronise before returning; *_dev entry
+ * points only enqueue work (results such as byte counts are written to device memory).
+ *
+ * There is NO CPU fallback: without a usable CUDA device jpezyb200_ctx_create fails with
+ * JPEZYB200_ENODEVICE and nothing else can be called.
+ */
+#ifndef JPEZY_B200_H
+#define JPEZY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define JPEZYB200_API __attribute__((visibility("default")))
+#else
+#define JPEZYB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JPEZYB200_ABI_VERSION 1
+
+/* status codes (reference: C++ exceptions / empty optional, SURVEY.md 8b "Errors") */
+enum {
+    JPEZYB200_OK = 0,
+    JPEZYB200_EINVAL = 1,       /* bad argument (null pointer, zero size, > 65535)                 */
+    JPEZYB200_ECAPACITY = 2,    /* output buffer too small (reference: bofstream overflow)         */
+    JPEZYB200_ECUDA = 3,        /* CUDA runtime error, see jpezyb200_last_error                   */
+    JPEZYB200_ENCCL = 4,        /* collective error (multi-GPU paths)                              */
+    JPEZYB200_ECORRUPT = 5,     /* entropy-coded segment cannot be decoded (reference: decode()
+                                   returns an empty optional, src/decoder/jpezy_decoder.hpp:109-114) */
+    JPEZYB200_ENODEVICE = 6,    /* no CUDA device: there is no CPU path                            */
+    JPEZYB200_ENOMEM = 7,
+    JPEZYB200_EUNSUPPORTED = 8  /* frame layout outside what the device decoder handles            */
+};
+
+typedef struct jpezyb200_ctx jpezyb200_ctx;
+
+/* One context per device; owns the device scratch (coefficients, bit lengths, scan state, the
+ * un-stuffed stream) and one stream.  Used by one host thread at a time. */
+JPEZYB200_API int jpezyb200_ctx_create(int device, jpezyb200_ctx** out);
+JPEZYB200_API void jpezyb200_ctx_destroy(jpezyb200_ctx* ctx);
+JPEZYB200_API const char* jpezyb200_strerror(int code);
+JPEZYB200_API const char* jpezyb200_last_error(const jpezyb200_ctx* ctx);
+JPEZYB200_API int jpezyb200_abi_version(void);
+
+/* options */
+enum {
+    JPEZYB200_OPT_PAD_ONES = 1,   /* fill bits of the last scan byte: 1 (default, T.81 F.1.2.3) or 0.
+                                     Replaces the padding decision inside srook::io::jpeg::bofstream
+                                     (call site src/encoder/jpezy_writer.hpp:101-105). */
+    JPEZYB200_OPT_TRANSFORM = 2   /* forward/inverse transform kernel variant: 0 = fast path with
+                                     guard band + exact recompute (default), 1 = FP64 separable
+                                     (validation build)                                           */
+};
+JPEZYB200_API int jpezyb200_set_option(jpezyb200_ctx* ctx, int option, int64_t value);
+
+/* statistics (monotonic counters since context creation) */
+enum {
+    JPEZYB200_STAT_KERNEL_LAUNCHES = 1,  /* number of kernels this library launched              */
+    JPEZYB200_STAT_GUARD_FWD = 2,        /* DCT coefficients re-computed in exact reference order */
+    JPEZYB200_STAT_GUARD_INV = 3,        /* IDCT samples re-computed in exact reference order     */
+    JPEZYB200_STAT_SYNC_ROUNDS = 4       /* self-synchronisation rounds of the last decode        */
+};
+JPEZYB200_API int jpezyb200_get_stat(jpezyb200_ctx* ctx, int stat, uint64_t* value);
+
+/* ------------------------------------------------------------------------------------------------
+ * Encoder.  Replaces the MCU loop of jpezy::encoder<T>::encode<MODE>()
+ * (src/encoder/jpezy_encoder.hpp:55-67: make_YCC :90-144, DCT :146-166, quantization :168-172,
+ * encode_huffman :174-225, make_MCU :227-242) together with the bit writer it drives
+ * (srook::io::jpeg::bofstream, call sites :189-220).  Produces ONLY the entropy-coded segment
+ * (byte-stuffed, last byte padded); the 644-byte header (src/encoder/jpezy_writer.hpp:20-94)
+ * and EOI (:101-105) stay with the host writer.
+ *
+ * r,g,b: planar 8-bit samples, W*H each, row stride W (src/encoder/jpezy_encoder.hpp:105).
+ * gray != 0 selects GRAY_MODE (:60-64: Cb/Cr blocks zeroed after colour conversion).
+ * ---------------------------------------------------------------------------------------------- */
+JPEZYB200_API int jpezyb200_encode(jpezyb200_ctx* ctx, const uint8_t* r, const uint8_t* g, const uint8_t* b, uint32_t W, uint32_t H,
+                     int gray, uint8_t* scan_out, size_t scan_cap, size_t* scan_bytes, uint64_t* scan_bits);
+
+/* Batch of nimg images of identical geometry, everything device resident.  Image i reads planes
+ * at d_r + i*W*H (etc.) and writes its segment at d_scan + i*slot_bytes; d_scan_bytes[i] /
+ * d_scan_bits[i] (device, may be NULL) receive the stuffed byte count / the un-stuffed bit count.
+ * A segment that does not fit in slot_bytes sets d_scan_bytes[i] = UINT64_MAX. */
+JPEZYB200_API int jpezyb200_encode_batch_dev(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g, const uint8_t* d_b, uint32_t W,
+                               uint32_t H, uint32_t nimg, int gray, uint8_t* d_scan, size_t slot_bytes,
+                               uint64_t* d_scan_bytes, uint64_t* d_scan_bits, void* stream);
+
+/* Stage E1+E2 only: planar RGB -> quantised coefficients, int16, zig-zag order
+ * (src/jpezy.hpp:36-45), block order Y0 Y1 Y2 Y3 Cb Cr per MCU, MCUs row-major
+ * (src/encoder/jpezy_encoder.hpp:227-242).  d_coefs holds nimg * num_mcus * 6 * 64 int16. */
+JPEZYB200_API int jpezyb200_transform_fwd_dev(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g, const uint8_t* d_b,
+                                uint32_t W, uint32_t H, uint32_t nimg, int gray, int16_t* d_coefs, void* stream);
+
+/* Stage E3 only: coefficients (layout above) -> stuffed, padded entropy segment(s)
+ * (src/encoder/jpezy_encoder.hpp:174-225).  Byte-identical to the reference given identical
+ * coefficients. */
+JPEZYB200_API int jpezyb200_entropy_encode_dev(jpezyb200_ctx* ctx, const int16_t* d_coefs, uint32_t W, uint32_t H, uint32_t nimg,
+                                 int gray, uint8_t* d_scan, size_t slot_bytes, uint64_t* d_scan_bytes,
+                                 uint64_t* d_scan_bits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoder.  Replaces the MCU loop of jpezy::decoder<BuildMode>::decode<MODE>()
+ * (src/decoder/jpezy_decoder.hpp:107-130: decode_mcu :504-528, decode_huffman :583-642,
+ * inverse_quantization :645-650, inverse_dct :652-670, make_rgb :531-578) and the bit reader
+ * (srook::io::jpeg::bifstream, call sites :589,612,634).  Marker parsing (:171-502) stays on the
+ * host and hands its result over in jpezyb200_frame.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct jpezyb200_huff {
+    uint8_t present;
+    uint8_t bits[16];   /* number of codes of length 1..16 (DHT, src/decoder/jpezy_decoder.hpp:208-211) */
+    uint8_t vals[256];  /* symbol values in code order (:240)                                         */
+} jpezyb200_huff;
+
+typedef struct jpezyb200_frame {
+    uint32_t width, height;        /* SOF0 (src/decoder/jpezy_decoder.hpp:286-289)                    */
+    uint8_t sample_precision;      /* 8                                                               */
+    uint8_t ncomp;                 /* 3 (1 is parsed by the host but not decoded on the device yet)   */
+    uint8_t hs[3], vs[3], tq[3];   /* Frame_component H, V, Tq (src/decoder/tables.hpp:18-21)         */
+    uint8_t td[3], ta[3];          /* Scan_component Td, Ta (:23-26); the reference uses Td for both  */
+    uint16_t restart_interval;     /* DRI (src/decoder/jpezy_decoder.hpp:400-404); must be 0          */
+    uint16_t qt[4][64];            /* natural order, as analyze_dqt stores them (:258-277)            */
+    jpezyb200_huff ht[2][4];       /* [class 0=DC,1=AC][id]                                           */
+} jpezyb200_frame;
+
+/* Length of each output plane exactly as the reference sizes it
+ * (src/decoder/jpezy_decoder.hpp:94-101): (v_unit*vmax*8) * (h_unit*hmax*8). */
+JPEZYB200_API size_t jpezyb200_plane_bytes(const jpezyb200_frame* f);
+/* Fill a frame descriptor with the layout and Annex K tables jpezy's own encoder writes. */
+JPEZYB200_API int jpezyb200_default_frame(uint32_t W, uint32_t H, jpezyb200_frame* f);
+
+/* scan: entropy-coded segment (everything after the SOS header; a trailing EOI marker is allowed).
+ * r,g,b: planes of plane_bytes each, row stride = width; rows >= height of the last MCU row land in
+ * the tail exactly as in make_rgb (:535-553); bytes never written are zero. */
+JPEZYB200_API int jpezyb200_decode(jpezyb200_ctx* ctx, const uint8_t* scan, size_t scan_bytes, const jpezyb200_frame* f, int gray,
+                     uint8_t* r, uint8_t* g, uint8_t* b, size_t plane_bytes);
+
+/* Batch, device resident, all images share the frame descriptor.  Image i: segment at
+ * d_scan + i*slot_bytes with length h_scan_bytes[i] (HOST array: the file length is host knowledge),
+ * planes at d_r + i*plane_bytes.  d_status[i] (device, may be NULL) receives 0 or JPEZYB200_ECORRUPT. */
+JPEZYB200_API int jpezyb200_decode_batch_dev(jpezyb200_ctx* ctx, const uint8_t* d_scan, size_t slot_bytes, const uint64_t* h_scan_bytes,
+                               uint32_t nimg, const jpezyb200_frame* f, int gray, uint8_t* d_r, uint8_t* d_g, uint8_t* d_b,
+                               size_t plane_bytes, int32_t* d_status, void* stream);
+
+/* Stage D1 only: segment(s) -> coefficients (layout of jpezyb200_transform_fwd_dev, DC absolute). */
+JPEZYB200_API int jpezyb200_entropy_decode_dev(jpezyb200_ctx* ctx, const uint8_t* d_scan, size_t slot_bytes,
+                                 const uint64_t* h_scan_bytes, uint32_t nimg, const jpezyb200_frame* f, int16_t* d_coefs,
+                                 int32_t* d_status, void* stream);
+
+/* Stage D2+D3 only: coefficients -> planar RGB. */
+JPEZYB200_API int jpezyb200_transform_inv_dev(jpezyb200_ctx* ctx, const int16_t* d_coefs, const jpezyb200_frame* f, uint32_t nimg,
+                                int gray, uint8_t* d_r, uint8_t* d_g, uint8_t* d_b, size_t plane_bytes, void* stream);
+
+/* Synthetic planar RGB generator, pure integer arithmetic, identical to
+ * jpezy_b200.synth on the host.  family: 0 = S-photo, 1 = S-noise, 2 = flat/ramps (adversarial). */
+JPEZYB200_API int jpezyb200_synth_dev(jpezyb200_ctx* ctx, uint8_t* d_r, uint8_t* d_g, uint8_t* d_b, uint32_t W, uint32_t H,
+                        uint32_t nimg, uint32_t first_frame, int family, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JPEZY_B200_H */

@@ -1,0 +1,334 @@
+// capi.cu -- the C ABI of libjpezy_b200.so (include/jpezy_b200.h): context, table upload,
+// kernel launches.  Single translation unit: all kernels are included here.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "dec_entropy.cuh"
+#include "dec_transform.cuh"
+#include "enc_entropy.cuh"
+#include "enc_transform.cuh"
+#include "synth.cuh"
+
+namespace jz {
+
+// canonical Huffman code construction (T.81 Annex C.2); the same thing the reference's decoder
+// does in analyze_dht (src/decoder/jpezy_decoder.hpp:223-239)
+static void canonical_codes(const uint8_t bits[16], const uint8_t* vals, int nvals, uint16_t code_of[256], uint8_t len_of[256])
+{
+    std::memset(code_of, 0, 256 * sizeof(uint16_t));
+    std::memset(len_of, 0, 256);
+    int code = 0, k = 0;
+    for (int len = 1; len <= 16; ++len) {
+        for (int j = 0; j < bits[len - 1] && k < nvals; ++j, ++k) {
+            code_of[vals[k]] = uint16_t(code++);
+            len_of[vals[k]] = uint8_t(len);
+        }
+        code <<= 1;
+    }
+}
+
+static void build_enc_lut(const HuffSpec& dc, const HuffSpec& ac, HuffEncLut* out)
+{
+    uint16_t code[256];
+    uint8_t len[256];
+    std::memset(out, 0, sizeof *out);
+    canonical_codes(dc.bits, dc.vals, dc.nvals, code, len);
+    for (int i = 0; i < 16; ++i) out->dc[i] = len[i] ? (uint32_t(code[i]) << 5) | len[i] : 0u;
+    canonical_codes(ac.bits, ac.vals, ac.nvals, code, len);
+    for (int i = 0; i < 256; ++i) out->ac[i] = len[i] ? (uint32_t(code[i]) << 5) | len[i] : 0u;
+}
+
+static cudaStream_t pick_stream(jpezyb200_ctx* ctx, void* s) { return s ? static_cast<cudaStream_t>(s) : ctx->stream; }
+
+}  // namespace jz
+
+using namespace jz;
+
+extern "C" {
+
+int jpezyb200_abi_version(void) { return JPEZYB200_ABI_VERSION; }
+
+const char* jpezyb200_strerror(int code)
+{
+    switch (code) {
+    case JPEZYB200_OK: return "ok";
+    case JPEZYB200_EINVAL: return "invalid argument";
+    case JPEZYB200_ECAPACITY: return "output buffer too small";
+    case JPEZYB200_ECUDA: return "CUDA error";
+    case JPEZYB200_ENCCL: return "collective error";
+    case JPEZYB200_ECORRUPT: return "corrupt entropy-coded segment";
+    case JPEZYB200_ENODEVICE: return "no CUDA device (libjpezy_b200 has no CPU path)";
+    case JPEZYB200_ENOMEM: return "out of memory";
+    case JPEZYB200_EUNSUPPORTED: return "unsupported frame layout";
+    default: return "unknown error";
+    }
+}
+
+const char* jpezyb200_last_error(const jpezyb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int jpezyb200_ctx_create(int device, jpezyb200_ctx** out)
+{
+    if (!out) return JPEZYB200_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return JPEZYB200_ENODEVICE;
+    }
+    if (device < 0 || device >= ndev) return JPEZYB200_EINVAL;
+    jpezyb200_ctx* ctx = new (std::nothrow) jpezyb200_ctx();
+    if (!ctx) return JPEZYB200_ENOMEM;
+    ctx->device = device;
+    int rc = [&]() -> int {
+        JZ_CUDA_TRY(ctx, cudaSetDevice(device));
+        JZ_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        DevConst h{};
+        for (int i = 0; i < 64; ++i) {
+            h.cos_ref[i] = kCosRef[i];
+            h.cosf_[i] = float(std::cos((2 * (i & 7) + 1) * (i >> 3) * 3.14159265358979323846 / 16));
+            h.quant[0][i] = kQuantLuma[i], h.quant[1][i] = kQuantChroma[i];
+            h.rquant[0][i] = 1.0f / float(kQuantLuma[i]), h.rquant[1][i] = 1.0f / float(kQuantChroma[i]);
+            h.zz[i] = kZigzag[i];
+            h.izz[kZigzag[i]] = uint8_t(i);
+        }
+        h.inv_sqrt2_ref = kInvSqrt2Ref;
+        JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(cC, &h, sizeof h));
+        HuffEncLut lut[2];
+        build_enc_lut(kDcLuma, kAcLuma, &lut[0]);
+        build_enc_lut(kDcChroma, kAcChroma, &lut[1]);
+        JZ_CUDA_TRY(ctx, cudaMalloc(&ctx->d_enc_lut, sizeof lut));
+        JZ_CUDA_TRY(ctx, cudaMemcpy(ctx->d_enc_lut, lut, sizeof lut, cudaMemcpyHostToDevice));
+        JZ_CUDA_TRY(ctx, cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
+        JZ_CUDA_TRY(ctx, cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)));
+        return JPEZYB200_OK;
+    }();
+    if (rc != JPEZYB200_OK) {
+        jpezyb200_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return JPEZYB200_OK;
+}
+
+void jpezyb200_ctx_destroy(jpezyb200_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    jz_devbuf* bufs[] = {&ctx->coefs, &ctx->blk_off, &ctx->tile_sum, &ctx->tile_base, &ctx->img_bits, &ctx->ustream,
+                         &ctx->ff_sum, &ctx->ff_base, &ctx->planes_in, &ctx->planes_out, &ctx->scan_io, &ctx->sizes_io,
+                         &ctx->dec_a, &ctx->dec_b, &ctx->dec_c, &ctx->dec_d, &ctx->dec_e};
+    for (jz_devbuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (ctx->d_enc_lut) cudaFree(ctx->d_enc_lut);
+    if (ctx->d_dec_lut) cudaFree(ctx->d_dec_lut);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int jpezyb200_set_option(jpezyb200_ctx* ctx, int option, int64_t value)
+{
+    if (!ctx) return JPEZYB200_EINVAL;
+    switch (option) {
+    case JPEZYB200_OPT_PAD_ONES: ctx->pad_ones = value ? 1 : 0; return JPEZYB200_OK;
+    case JPEZYB200_OPT_TRANSFORM: ctx->transform_variant = int(value); return JPEZYB200_OK;
+    default: return ctx->fail(JPEZYB200_EINVAL, "unknown option");
+    }
+}
+
+int jpezyb200_get_stat(jpezyb200_ctx* ctx, int stat, uint64_t* value)
+{
+    if (!ctx || !value) return JPEZYB200_EINVAL;
+    if (stat == JPEZYB200_STAT_KERNEL_LAUNCHES) {
+        *value = ctx->launches;
+        return JPEZYB200_OK;
+    }
+    int idx = stat == JPEZYB200_STAT_GUARD_FWD ? 0 : stat == JPEZYB200_STAT_GUARD_INV ? 1 : stat == JPEZYB200_STAT_SYNC_ROUNDS ? 2 : -1;
+    if (idx < 0) return ctx->fail(JPEZYB200_EINVAL, "unknown stat");
+    JZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    unsigned long long v = 0;
+    JZ_CUDA_TRY(ctx, cudaMemcpy(&v, ctx->d_counters + idx, sizeof v, cudaMemcpyDeviceToHost));
+    *value = v;
+    return JPEZYB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// encoder
+// -------------------------------------------------------------------------------------------------
+static int check_geometry(jpezyb200_ctx* ctx, uint32_t W, uint32_t H, uint32_t nimg)
+{
+    if (!ctx) return JPEZYB200_EINVAL;
+    // SOF0 carries 16-bit sizes (src/encoder/jpezy_writer.hpp:70-71)
+    if (W == 0 || H == 0 || W > 65535u || H > 65535u) return ctx->fail(JPEZYB200_EINVAL, "width/height must be in 1..65535");
+    if (nimg == 0 || nimg > 65535u) return ctx->fail(JPEZYB200_EINVAL, "nimg must be in 1..65535");
+    return JPEZYB200_OK;
+}
+
+static int launch_fwd(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g, const uint8_t* d_b, uint32_t W, uint32_t H,
+                      uint32_t nimg, int gray, int16_t* d_coefs, cudaStream_t st)
+{
+    FwdParams p{};
+    p.r = d_r, p.g = d_g, p.b = d_b;
+    p.plane_stride = size_t(W) * H;
+    p.W = W, p.H = H;
+    p.HU = mcu_units(W), p.VU = mcu_units(H);
+    p.coefs = d_coefs;
+    p.coef_stride = size_t(p.HU) * p.VU * 384;
+    p.row0 = 0, p.y_origin = 0;
+    p.gray = gray;
+    p.guard_counter = ctx->d_counters + 0;
+    dim3 grid((p.HU + kMcuPerCta - 1) / kMcuPerCta, p.VU, nimg);
+    k_fwd_transform_f64<<<grid, kFwdThreads, 0, st>>>(p);
+    ++ctx->launches;
+    JZ_CUDA_TRY(ctx, cudaGetLastError());
+    return JPEZYB200_OK;
+}
+
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int launch_entropy(jpezyb200_ctx* ctx, const int16_t* d_coefs, uint32_t W, uint32_t H, uint32_t nimg, uint8_t* d_scan,
+                          size_t slot_bytes, uint64_t* d_scan_bytes, uint64_t* d_scan_bits, cudaStream_t st)
+{
+    const uint32_t HU = mcu_units(W), VU = mcu_units(H);
+    const size_t nmcu = size_t(HU) * VU;
+    if (nmcu * 6 > 0xffffff00ull) return ctx->fail(JPEZYB200_EINVAL, "too many blocks");
+    EntParams p{};
+    p.coefs = d_coefs;
+    p.coef_stride = nmcu * 384;
+    p.nblk = uint32_t(nmcu * 6);
+    p.ntile = (p.nblk + kEntThreads - 1) / kEntThreads;
+    p.uslot = round_up(slot_bytes + 64, 16);
+    p.nchunk = uint32_t((p.uslot + kStuffChunk - 1) / kStuffChunk) + 1;
+    p.slot = slot_bytes;
+    p.out = d_scan;
+    p.out_bytes = d_scan_bytes, p.out_bits = d_scan_bits;
+    p.lut = ctx->d_enc_lut;
+    p.dc_init = nullptr;
+    p.pad_ones = ctx->pad_ones;
+    int rc;
+    if ((rc = ctx->ensure(ctx->blk_off, size_t(nimg) * p.nblk * 4))) return rc;
+    if ((rc = ctx->ensure(ctx->tile_sum, size_t(nimg) * p.ntile * 4))) return rc;
+    if ((rc = ctx->ensure(ctx->tile_base, size_t(nimg) * p.ntile * 8))) return rc;
+    if ((rc = ctx->ensure(ctx->img_bits, size_t(nimg) * 16))) return rc;
+    if ((rc = ctx->ensure(ctx->ustream, size_t(nimg) * p.uslot))) return rc;
+    if ((rc = ctx->ensure(ctx->ff_sum, size_t(nimg) * p.nchunk * 4))) return rc;
+    if ((rc = ctx->ensure(ctx->ff_base, size_t(nimg) * p.nchunk * 8))) return rc;
+    p.blk_off = static_cast<uint32_t*>(ctx->blk_off.p);
+    p.tile_sum = static_cast<uint32_t*>(ctx->tile_sum.p);
+    p.tile_base = static_cast<uint64_t*>(ctx->tile_base.p);
+    p.img_bits = static_cast<uint64_t*>(ctx->img_bits.p);
+    p.img_bytes = p.img_bits + nimg;
+    p.ustream = static_cast<uint8_t*>(ctx->ustream.p);
+    p.ff_sum = static_cast<uint32_t*>(ctx->ff_sum.p);
+    p.ff_base = static_cast<uint64_t*>(ctx->ff_base.p);
+
+    k_block_bits<<<dim3(p.ntile, nimg), kEntThreads, 0, st>>>(p);
+    k_scan_tiles<<<nimg, 1024, 0, st>>>(p);
+    // grid-stride helpers: enough CTAs to fill the machine, split evenly over the images
+    const uint32_t per_img = std::max<uint32_t>(1u, std::min<uint32_t>(p.nchunk, (148u * 8u + nimg - 1) / nimg));
+    k_zero_ustream<<<dim3(per_img, nimg), 256, 0, st>>>(p);
+    k_scatter<<<dim3(p.ntile, nimg), kEntThreads, 0, st>>>(p);
+    k_ff_count<<<dim3(per_img, nimg), kStuffThreads, 0, st>>>(p);
+    k_scan_ff<<<nimg, 1024, 0, st>>>(p);
+    k_stuff_write<<<dim3(per_img, nimg), kStuffThreads, 0, st>>>(p);
+    ctx->launches += 7;
+    JZ_CUDA_TRY(ctx, cudaGetLastError());
+    return JPEZYB200_OK;
+}
+
+int jpezyb200_transform_fwd_dev(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g, const uint8_t* d_b, uint32_t W,
+                                uint32_t H, uint32_t nimg, int gray, int16_t* d_coefs, void* stream)
+{
+    int rc = check_geometry(ctx, W, H, nimg);
+    if (rc) return rc;
+    if (!d_r || !d_g || !d_b || !d_coefs) return ctx->fail(JPEZYB200_EINVAL, "null pointer");
+    JZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return launch_fwd(ctx, d_r, d_g, d_b, W, H, nimg, gray, d_coefs, pick_stream(ctx, stream));
+}
+
+int jpezyb200_entropy_encode_dev(jpezyb200_ctx* ctx, const int16_t* d_coefs, uint32_t W, uint32_t H, uint32_t nimg, int gray,
+                                 uint8_t* d_scan, size_t slot_bytes, uint64_t* d_scan_bytes, uint64_t* d_scan_bits, void* stream)
+{
+    (void)gray;
+    int rc = check_geometry(ctx, W, H, nimg);
+    if (rc) return rc;
+    if (!d_coefs || !d_scan || slot_bytes == 0) return ctx->fail(JPEZYB200_EINVAL, "null pointer / empty slot");
+    JZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return launch_entropy(ctx, d_coefs, W, H, nimg, d_scan, slot_bytes, d_scan_bytes, d_scan_bits, pick_stream(ctx, stream));
+}
+
+int jpezyb200_encode_batch_dev(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g, const uint8_t* d_b, uint32_t W,
+                               uint32_t H, uint32_t nimg, int gray, uint8_t* d_scan, size_t slot_bytes, uint64_t* d_scan_bytes,
+                               uint64_t* d_scan_bits, void* stream)
+{
+    int rc = check_geometry(ctx, W, H, nimg);
+    if (rc) return rc;
+    if (!d_r || !d_g || !d_b || !d_scan || slot_bytes == 0) return ctx->fail(JPEZYB200_EINVAL, "null pointer / empty slot");
+    JZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t ncoef = size_t(mcu_units(W)) * mcu_units(H) * 384 * nimg;
+    if ((rc = ctx->ensure(ctx->coefs, ncoef * sizeof(int16_t)))) return rc;
+    cudaStream_t st = pick_stream(ctx, stream);
+    if ((rc = launch_fwd(ctx, d_r, d_g, d_b, W, H, nimg, gray, static_cast<int16_t*>(ctx->coefs.p), st))) return rc;
+    return launch_entropy(ctx, static_cast<int16_t*>(ctx->coefs.p), W, H, nimg, d_scan, slot_bytes, d_scan_bytes, d_scan_bits, st);
+}
+
+int jpezyb200_encode(jpezyb200_ctx* ctx, const uint8_t* r, const uint8_t* g, const uint8_t* b, uint32_t W, uint32_t H, int gray,
+                     uint8_t* scan_out, size_t scan_cap, size_t* scan_bytes, uint64_t* scan_bits)
+{
+    int rc = check_geometry(ctx, W, H, 1);
+    if (rc) return rc;
+    if (!r || !g || !b || !scan_out || !scan_bytes || scan_cap == 0) return ctx->fail(JPEZYB200_EINVAL, "null pointer / empty buffer");
+    JZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t npx = size_t(W) * H;
+    if ((rc = ctx->ensure(ctx->planes_in, 3 * npx))) return rc;
+    if ((rc = ctx->ensure(ctx->scan_io, scan_cap))) return rc;
+    if ((rc = ctx->ensure(ctx->sizes_io, 64))) return rc;
+    uint8_t* d_in = static_cast<uint8_t*>(ctx->planes_in.p);
+    uint64_t* d_sz = static_cast<uint64_t*>(ctx->sizes_io.p);
+    cudaStream_t st = ctx->stream;
+    JZ_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, r, npx, cudaMemcpyHostToDevice, st));
+    JZ_CUDA_TRY(ctx, cudaMemcpyAsync(d_in + npx, g, npx, cudaMemcpyHostToDevice, st));
+    JZ_CUDA_TRY(ctx, cudaMemcpyAsync(d_in + 2 * npx, b, npx, cudaMemcpyHostToDevice, st));
+    rc = jpezyb200_encode_batch_dev(ctx, d_in, d_in + npx, d_in + 2 * npx, W, H, 1, gray, static_cast<uint8_t*>(ctx->scan_io.p),
+                                    scan_cap, d_sz, d_sz + 1, st);
+    if (rc) return rc;
+    uint64_t h_sz[2] = {0, 0};
+    JZ_CUDA_TRY(ctx, cudaMemcpyAsync(h_sz, d_sz, sizeof h_sz, cudaMemcpyDeviceToHost, st));
+    JZ_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (h_sz[0] == ~0ull || h_sz[0] > scan_cap) return ctx->fail(JPEZYB200_ECAPACITY, "entropy-coded segment does not fit in scan_cap");
+    JZ_CUDA_TRY(ctx, cudaMemcpyAsync(scan_out, ctx->scan_io.p, h_sz[0], cudaMemcpyDeviceToHost, st));
+    JZ_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    *scan_bytes = size_t(h_sz[0]);
+    if (scan_bits) *scan_bits = h_sz[1];
+    return JPEZYB200_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// synthetic input
+// -------------------------------------------------------------------------------------------------
+int jpezyb200_synth_dev(jpezyb200_ctx* ctx, uint8_t* d_r, uint8_t* d_g, uint8_t* d_b, uint32_t W, uint32_t H, uint32_t nimg,
+                        uint32_t first_frame, int family, void* stream)
+{
+    int rc = check_geometry(ctx, W, H, nimg);
+    if (rc) return rc;
+    if (!d_r || !d_g || !d_b) return ctx->fail(JPEZYB200_EINVAL, "null pointer");
+    JZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t npx = size_t(W) * H;
+    const uint32_t gx = uint32_t(std::min<size_t>((npx + 255) / 256, 148 * 16));
+    k_synth<<<dim3(gx, nimg), 256, 0, pick_stream(ctx, stream)>>>(d_r, d_g, d_b, W, H, first_frame, family);
+    ++ctx->launches;
+    JZ_CUDA_TRY(ctx, cudaGetLastError());
+    return JPEZYB200_OK;
+}
+
+}  // extern "C"
+
+#include "capi_decode.inc"

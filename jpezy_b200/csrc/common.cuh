@@ -1,0 +1,125 @@
+// common.cuh -- device-side constants, small helpers and the context of libjpezy_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/jpezy_b200.h"
+#include "tables.h"
+
+namespace jz {
+
+// ---------------------------------------------------------------------------------------------
+// Constant bank: everything the transform kernels index with compile-time (uniform) indices.
+// ---------------------------------------------------------------------------------------------
+struct DevConst {
+    double cos_ref[64];    // the reference's table, used by the exact-order recompute path
+    double inv_sqrt2_ref;  // 1.0/sqrt(2.0) as the reference evaluates it
+    float cosf_[64];       // ideal cosines in float (fast paths)
+    uint16_t quant[2][64]; // [0]=luma, [1]=chroma, natural order (Annex K, src/jpezy.hpp:131-152)
+    float rquant[2][64];   // 1/q
+    uint8_t zz[64];        // zig-zag position -> natural position (src/jpezy.hpp:36-45)
+    uint8_t izz[64];       // natural position -> zig-zag position
+};
+static __constant__ DevConst cC;   // single translation unit (capi.cu)
+
+// Huffman encoder LUT, one per table class (0 = luma tables, 1 = chroma tables).
+// ac[(run << 4) | size] and dc[category]; entry = (code << 5) | length, 0 = invalid.
+struct HuffEncLut {
+    uint32_t ac[256];
+    uint32_t dc[16];
+};
+
+// Huffman decoder LUT for one DHT table: 16-bit peek -> (length << 8) | symbol ; length 0 = invalid
+struct HuffDecLut {
+    uint16_t e[65536];
+};
+
+// number of 16x16 MCUs along one dimension
+__host__ __device__ inline uint32_t mcu_units(uint32_t n) { return (n + 15u) >> 4; }
+
+__device__ __forceinline__ int bit_length(int a)  // number of significant bits of a >= 0
+{
+    return 32 - __clz(a);
+}
+
+#define JZ_CUDA_TRY(ctx, expr)                                                                  \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) return (ctx)->fail_cuda(e__, #expr, __LINE__);                  \
+    } while (0)
+
+}  // namespace jz
+
+// Growable device buffer owned by the context
+struct jz_devbuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct jpezyb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int pad_ones = 1;
+    int transform_variant = 0;
+    uint64_t launches = 0;
+
+    // device-resident tables
+    jz::HuffEncLut* d_enc_lut = nullptr;  // [2]
+    // decoder LUTs are built per frame descriptor (cached by hash)
+    jz::HuffDecLut* d_dec_lut = nullptr;  // [4]: dc0, dc1, ac0, ac1 (selected by td/ta)
+    uint64_t dec_lut_key = 0;
+
+    // counters on the device: [0] guard_fwd, [1] guard_inv, [2] sync rounds, [3] scratch
+    unsigned long long* d_counters = nullptr;
+
+    // scratch
+    jz_devbuf coefs, blk_off, tile_sum, tile_base, img_bits, ustream, ff_sum, ff_base, planes_in, planes_out, scan_io, sizes_io;
+    jz_devbuf dec_a, dec_b, dec_c, dec_d, dec_e;
+    void* h_pinned = nullptr;
+    size_t h_pinned_cap = 0;
+
+    int fail_cuda(cudaError_t e, const char* what, int line)
+    {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s [capi.cu:%d]", int(e), cudaGetErrorString(e), what, line);
+        err = buf;
+        cudaGetLastError();
+        return JPEZYB200_ECUDA;
+    }
+    int fail(int code, const char* msg)
+    {
+        err = msg;
+        return code;
+    }
+    int ensure(jz_devbuf& b, size_t bytes)
+    {
+        if (bytes <= b.cap) return JPEZYB200_OK;
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr, b.cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            err = "cudaMalloc failed for scratch buffer";
+            return JPEZYB200_ENOMEM;
+        }
+        b.cap = want;
+        return JPEZYB200_OK;
+    }
+    int ensure_pinned(size_t bytes)
+    {
+        if (bytes <= h_pinned_cap) return JPEZYB200_OK;
+        if (h_pinned) cudaFreeHost(h_pinned);
+        h_pinned = nullptr, h_pinned_cap = 0;
+        if (cudaMallocHost(&h_pinned, bytes + 4096) != cudaSuccess) {
+            cudaGetLastError();
+            err = "cudaMallocHost failed";
+            return JPEZYB200_ENOMEM;
+        }
+        h_pinned_cap = bytes + 4096;
+        return JPEZYB200_OK;
+    }
+};
