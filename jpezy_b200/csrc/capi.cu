@@ -123,7 +123,8 @@ void jpezyb200_ctx_destroy(jpezyb200_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     jz_devbuf* bufs[] = {&ctx->coefs, &ctx->blk_off, &ctx->tile_sum, &ctx->tile_base, &ctx->img_bits, &ctx->ustream,
                          &ctx->ff_sum, &ctx->ff_base, &ctx->planes_in, &ctx->planes_out, &ctx->scan_io, &ctx->sizes_io,
-                         &ctx->dec_a, &ctx->dec_b, &ctx->dec_c, &ctx->dec_d, &ctx->dec_e};
+                         &ctx->dec_scanbytes, &ctx->dec_chunk_cnt, &ctx->dec_chunk_base, &ctx->dec_ubytes, &ctx->dec_state,
+                         &ctx->dec_dirty, &ctx->dec_subblk, &ctx->dec_dc, &ctx->dec_status};
     for (jz_devbuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_enc_lut) cudaFree(ctx->d_enc_lut);

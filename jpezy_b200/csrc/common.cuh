@@ -31,10 +31,6 @@ struct HuffEncLut {
     uint32_t dc[16];
 };
 
-// Huffman decoder LUT for one DHT table: 16-bit peek -> (length << 8) | symbol ; length 0 = invalid
-struct HuffDecLut {
-    uint16_t e[65536];
-};
 
 // number of 16x16 MCUs along one dimension
 __host__ __device__ inline uint32_t mcu_units(uint32_t n) { return (n + 15u) >> 4; }
@@ -68,8 +64,8 @@ struct jpezyb200_ctx {
 
     // device-resident tables
     jz::HuffEncLut* d_enc_lut = nullptr;  // [2]
-    // decoder LUTs are built per frame descriptor (cached by hash)
-    jz::HuffDecLut* d_dec_lut = nullptr;  // [4]: dc0, dc1, ac0, ac1 (selected by td/ta)
+    // decoder tables are built per frame descriptor (cached by hash): [4] = DC luma, DC chroma, AC luma, AC chroma
+    void* d_dec_lut = nullptr;
     uint64_t dec_lut_key = 0;
 
     // counters on the device: [0] guard_fwd, [1] guard_inv, [2] sync rounds, [3] scratch
@@ -77,7 +73,7 @@ struct jpezyb200_ctx {
 
     // scratch
     jz_devbuf coefs, blk_off, tile_sum, tile_base, img_bits, ustream, ff_sum, ff_base, planes_in, planes_out, scan_io, sizes_io;
-    jz_devbuf dec_a, dec_b, dec_c, dec_d, dec_e;
+    jz_devbuf dec_scanbytes, dec_chunk_cnt, dec_chunk_base, dec_ubytes, dec_state, dec_dirty, dec_subblk, dec_dc, dec_status;
     void* h_pinned = nullptr;
     size_t h_pinned_cap = 0;
 

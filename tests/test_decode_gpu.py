@@ -1,0 +1,161 @@
+"""-m gpu parity tests of the decoder path (C ABI -> CUDA kernels) against the CPU oracle.
+
+Bars: the parallel (self-synchronising) Huffman decoder reproduces the sequential decoder's coefficients
+exactly; decoded pixels may differ from the reference decoder by at most 1 (BASELINE.json) -- with the
+exact-order recompute of boundary samples the expected number of differing samples is 0 and is reported.
+"""
+import numpy as np
+import pytest
+import torch
+
+import jpezy_b200 as J
+from jpezy_b200 import capi
+from gpu_util import planes, to_dev
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(64, 48), (200, 120), (1, 1), (17, 33), (16, 16), (250, 7), (512, 512)]
+
+
+def split(f):
+    assert f[:2] == b"\xff\xd8" and f[-2:] == b"\xff\xd9"
+    return f[644:-2]
+
+
+def gpu_entropy_decode(ctx, scans, W, H):
+    frame = J.default_frame(W, H)
+    n = len(scans)
+    slot = max(len(s) for s in scans) + 16
+    buf = np.zeros((n, slot), dtype=np.uint8)
+    for i, s in enumerate(scans):
+        buf[i, : len(s)] = np.frombuffer(s, dtype=np.uint8)
+    d = to_dev(buf)
+    nm = capi.num_mcus(W, H)
+    dc = torch.full((n, nm, 6, 64), 777, dtype=torch.int16, device="cuda")
+    st = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    ctx.entropy_decode_dev(d, slot, [len(s) for s in scans], n, frame, dc, st, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return dc.cpu().numpy(), st.cpu().numpy()
+
+
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("family", [0, 1, 2])
+def test_entropy_decode_matches_sequential_decoder(ctx, oracle, W, H, family):
+    r, g, b = planes(family, W, H)
+    f = oracle.encode(r, g, b, W, H)
+    want = oracle.decode_coefs(f)
+    got, st = gpu_entropy_decode(ctx, [split(f)], W, H)
+    assert st[0] == 0
+    assert (got[0] == want).all()
+
+
+def test_entropy_decode_with_trailing_eoi_and_batch(ctx, oracle):
+    W, H = 136, 72
+    files = [oracle.encode(*planes(fam, W, H, frame=k), W, H) for k, fam in enumerate([0, 1, 2, 1, 0])]
+    scans = [f[644:] for f in files]          # keep the EOI marker: bytes after the last MCU are ignored
+    got, st = gpu_entropy_decode(ctx, scans, W, H)
+    for i, f in enumerate(files):
+        assert st[i] == 0 and (got[i] == oracle.decode_coefs(f)).all()
+
+
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("family", [0, 1, 2])
+@pytest.mark.parametrize("gray", [False, True])
+def test_decode_pixels(ctx, oracle, W, H, family, gray):
+    r, g, b = planes(family, W, H)
+    f = oracle.encode(r, g, b, W, H)
+    _, _, R0, G0, B0 = oracle.decode(f, gray=gray)
+    R, G, B = ctx.decode(split(f), J.default_frame(W, H), gray=gray)
+    assert R.size == R0.size
+    d = [np.abs(a.astype(int) - b0) for a, b0 in ((R, R0), (G, G0), (B, B0))]
+    nd = sum(int((x != 0).sum()) for x in d)
+    assert max(int(x.max()) for x in d) <= 1, "decoded pixels differ from the reference decoder by more than 1"
+    assert nd == 0, "%d samples differ by 1 (allowed by the contract, but the guard path should make it 0)" % nd
+
+
+def test_inverse_guard_path_is_exercised(ctx, oracle):
+    W, H = 256, 64
+    r, g, b = planes(2, W, H)       # flat tiles: DC-only blocks whose exact IDCT value is an integer
+    f = oracle.encode(r, g, b, W, H)
+    before = ctx.stat(capi.STAT_GUARD_INV)
+    R, G, B = ctx.decode(split(f), J.default_frame(W, H))
+    _, _, R0, G0, B0 = oracle.decode(f)
+    assert (R == R0).all() and (G == G0).all() and (B == B0).all()
+    assert ctx.stat(capi.STAT_GUARD_INV) > before
+
+
+def test_roundtrip_gpu_encode_gpu_decode(ctx, oracle):
+    W, H = 640, 360
+    r, g, b = planes(0, W, H)
+    scan, _ = ctx.encode(r, g, b, W, H)
+    R, G, B = ctx.decode(scan, J.default_frame(W, H))
+    _, _, R0, G0, B0 = oracle.decode(oracle.header(W, H) + scan + b"\xff\xd9")
+    assert (R == R0).all() and (G == G0).all() and (B == B0).all()
+    err = np.abs(R[: W * H].reshape(H, W).astype(int) - r).mean()
+    assert err < 8.0
+
+
+def test_padded_rows_and_tail(ctx, oracle):
+    # 1080-style geometry: H not a multiple of 16 -> rows >= H of the last MCU row land in the tail (make_rgb :535-553)
+    W, H = 40, 25
+    r, g, b = planes(0, W, H)
+    f = oracle.encode(r, g, b, W, H)
+    _, _, R0, _, _ = oracle.decode(f)
+    R, _, _ = ctx.decode(split(f), J.default_frame(W, H))
+    assert R.size == 48 * 32 and (R == R0).all()
+    assert (R[32 * 40:] == 0).all() and R[25 * 40: 32 * 40].any()
+
+
+def test_truncated_stream_is_reported_corrupt(ctx, oracle):
+    W, H = 128, 64
+    r, g, b = planes(1, W, H)
+    scan = split(oracle.encode(r, g, b, W, H))
+    with pytest.raises(J.JpezyError) as e:
+        ctx.decode(scan[: len(scan) // 3], J.default_frame(W, H))
+    assert e.value.code == capi.ECORRUPT
+
+
+def test_unsupported_layouts_are_refused(ctx):
+    f = J.default_frame(64, 64)
+    f.restart_interval = 4
+    with pytest.raises(J.JpezyError) as e:
+        ctx.decode(b"\x00" * 64, f)
+    assert e.value.code == capi.EUNSUPPORTED
+    f = J.default_frame(64, 64)
+    f.hs[0] = 1
+    with pytest.raises(J.JpezyError) as e:
+        ctx.decode(b"\x00" * 64, f)
+    assert e.value.code == capi.EUNSUPPORTED
+
+
+def test_custom_quant_and_huffman_tables_are_data(ctx, oracle):
+    # the decoder takes its tables from the frame descriptor: swapping the luma/chroma table ids must still decode
+    W, H = 96, 64
+    r, g, b = planes(0, W, H)
+    f = oracle.encode(r, g, b, W, H)
+    fr = J.default_frame(W, H)
+    got = ctx.decode(split(f), fr)
+    # permute table slots: put luma tables in id 2, chroma in id 3 and point the selectors there
+    fr2 = J.default_frame(W, H)
+    for tc in range(2):
+        fr2.ht[tc][2] = fr.ht[tc][0]
+        fr2.ht[tc][3] = fr.ht[tc][1]
+    for i in range(64):
+        fr2.qt[2][i] = fr.qt[0][i]
+        fr2.qt[3][i] = fr.qt[1][i]
+    fr2.td[0] = fr2.ta[0] = 2
+    fr2.td[1] = fr2.ta[1] = fr2.td[2] = fr2.ta[2] = 3
+    fr2.tq[0] = 2
+    fr2.tq[1] = fr2.tq[2] = 3
+    got2 = ctx.decode(split(f), fr2)
+    assert all((a == b2).all() for a, b2 in zip(got, got2))
+
+
+def test_sync_rounds_reported(ctx, oracle):
+    W, H = 512, 512
+    r, g, b = planes(0, W, H)
+    f = oracle.encode(r, g, b, W, H)
+    gpu_entropy_decode(ctx, [split(f)], W, H)
+    rounds = ctx.stat(capi.STAT_SYNC_ROUNDS)
+    print("self-synchronisation rounds for 512x512 S-photo:", rounds)
+    assert 1 <= rounds < 200
