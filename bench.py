@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- encode+decode MPix/s of the jpezy hot path on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl reference]
+
+A step = one pass of the hot path over one batch of synthetic input per GPU:
+  c2 (default, BASELINE.json configs[1]): one 3840x2160 RGB image, encode then decode
+  c3: a batch of 1920x1080 frames per GPU (configs[2] sharded by image; --batch frames per GPU)
+  c4: one 8192x8192 image in --gray mode (configs[3])
+`value` is device-timed (CUDA events, inputs resident in HBM, max over ranks); `e2e` is the same metric
+through the host-buffer C-ABI calls (jpezyb200_encode / jpezyb200_decode) with pinned host buffers and the
+H2D/D2H copies inside the timed region.  L2: inputs/outputs rotate through a ring of distinct frames whose
+footprint exceeds the 126 MB L2 (see config.l2).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2": dict(W=3840, H=2160, batch=1, gray=False, name="C2: single 3840x2160 RGB image, encode+decode round trip"),
+    "c3": dict(W=1920, H=1080, batch=64, gray=False, name="C3: batch of 1920x1080 RGB frames sharded by image, encode+decode"),
+    "c4": dict(W=8192, H=8192, batch=1, gray=True, name="C4: single 8192x8192 --gray image, encode+decode"),
+    "c1": dict(W=512, H=512, batch=1, gray=False, name="C1: single 512x512 RGB image, encode+decode"),
+}
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons of one GPU every 20 ms through NVML while the bench runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag, self.ok = index, [], set(), None, False, False
+        self.mark = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                if self.mark is not None:
+                    self.samples.append(mhz)
+                    for k, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: the reference itself
+    needs SrookCppLibraries/Boost) on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import jpezy_b200 as J
+    import oracle as orc
+    orc.build()
+    o = orc.Oracle("shipped")      # the reference's Release flags (compiler_settings.cmake:4)
+    cores = os.cpu_count() or 1
+    W, H = wl["W"], wl["H"]
+    # bounded sample: a band of MCU rows of the workload image, sized for ~120 s total at ~2.7 MPix/s/core round trip
+    budget_px = 120.0 / max(1, args.steps + args.warmup) * 2.7e6
+    rows = int(min(H, max(16, (budget_px // W) // 16 * 16)))
+    r, g, b = J.synth.image(0, W, rows, frame=0)
+    for _ in range(args.warmup):
+        o.time_roundtrip(r, g, b, W, rows, wl["gray"], 1, cores)
+    t0 = time.perf_counter()
+    te = td = 0.0
+    for _ in range(args.steps):
+        _, e, d = o.time_roundtrip(r, g, b, W, rows, wl["gray"], 1, cores)
+        te += e
+        td += d
+    dt = time.perf_counter() - t0
+    px = float(W) * rows * cores * args.steps
+    val = px / dt / 1e6
+    sample = "%dx%d band (%d of %d rows) of the workload image, one instance per core, encode()+decode() in memory" % (W, rows, rows, H)
+    line = {"impl": "reference", "metric": "encode+decode MPix/s", "value": val, "unit": "MPix/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"], "width": W, "height": H, "batch_per_gpu": wl["batch"], "gray": wl["gray"],
+                       "family": "S-photo"},
+            "cpu_baseline": {"value": val, "unit": "MPix/s", "cores": cores, "kind": "port", "sample": sample,
+                             "encode_MPix_s": px / (te / 1.0) / 1e6 * 1.0 if te else None,
+                             "decode_MPix_s": px / (td / 1.0) / 1e6 * 1.0 if td else None},
+            "e2e": {"value": val, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step (c3)")
+    ap.add_argument("--family", type=int, default=0, help="0 S-photo, 1 S-noise")
+    ap.add_argument("--ring", type=int, default=None, help="distinct input/output frame sets rotated between steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["batch"] = args.batch
+    if args.impl == "reference":
+        args.steps = args.steps or 5
+        args.warmup = args.warmup if args.warmup is not None else 1
+        return run_reference(args, wl)
+    args.steps = args.steps or 200
+    args.warmup = args.warmup if args.warmup is not None else 10
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import jpezy_b200 as J
+    from jpezy_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = J.Context(local_rank)
+    # a real (non-default) stream: the C ABI treats a NULL stream as "the context's own stream"
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sp = stream.cuda_stream
+    assert sp != 0
+
+    W, H, B, gray = wl["W"], wl["H"], wl["batch"], wl["gray"]
+    npx = W * H
+    frame = J.default_frame(W, H)
+    plane_len = J.plane_bytes(frame)
+    in_bytes = 3 * npx * B
+    out_bytes = 3 * plane_len * B
+    ring = args.ring or max(2, -(-300_000_000 // (in_bytes + out_bytes)))      # > 126 MB L2 with margin
+    slot = max(npx, 65536)        # bytes per image for the entropy-coded segment (1 B/px; ~0.05-0.35 B/px needed)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- synthetic inputs, generated on the device, checked against the host twin on one frame ----
+    d_in = torch.empty((ring, 3, B, H, W), dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros((ring, 3, B, plane_len), dtype=torch.uint8, device="cuda")
+    d_scan = torch.zeros((ring, B, slot), dtype=torch.uint8, device="cuda")
+    d_nbytes = torch.zeros((ring, B), dtype=torch.int64, device="cuda")
+    d_status = torch.zeros((ring, B), dtype=torch.int32, device="cuda")
+    for k in range(ring):
+        ctx.synth_dev(d_in[k, 0], d_in[k, 1], d_in[k, 2], W, H, nimg=B, first_frame=(rank * ring + k) * B, family=args.family, stream=sp)
+    torch.cuda.synchronize()
+    if rank == 0:
+        chk = J.synth.plane(args.family, W, min(H, 64), 0, 1)
+        assert (d_in[0, 1, 0, : chk.shape[0]].cpu().numpy() == chk).all(), "device synth != host synth"
+
+    h_nbytes = [None] * ring
+
+    def step(k):
+        ctx.encode_batch_dev(d_in[k, 0], d_in[k, 1], d_in[k, 2], W, H, B, gray, d_scan[k], slot, d_nbytes[k], None, stream=sp)
+        nb = d_nbytes[k].cpu().numpy().astype(np.uint64)        # the decoder's input length is host knowledge (file size)
+        h_nbytes[k] = nb
+        ctx.decode_batch_dev(d_scan[k], slot, nb, B, frame, gray, d_out[k, 0], d_out[k, 1], d_out[k, 2], plane_len, d_status[k], stream=sp)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, ring)):      # every ring slot is produced at least once before timing
+        step(i % ring)
+    barrier()
+    assert int(d_status.abs().sum().item()) == 0, "decode reported a corrupt stream"
+    assert int((d_nbytes[: min(ring, args.warmup)] < 0).sum().item()) == 0, "entropy-coded segment overflowed its slot"
+
+    sampler.mark = True
+    l0 = ctx.stat(capi.STAT_KERNEL_LAUNCHES)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i % ring)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.stat(capi.STAT_KERNEL_LAUNCHES) - l0
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * npx * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- per-stage device times + roofline of the dominant kernel (forward transform), same ring ----
+    nm = capi.num_mcus(W, H)
+    d_coefs = torch.empty((ring, B, nm, 6, 64), dtype=torch.int16, device="cuda")
+
+    def timed(fn, iters):
+        for i in range(3):
+            fn(i % ring)
+        torch.cuda.synchronize()
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for i in range(iters):
+            fn(i % ring)
+        b2.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b2) / iters
+
+    it = max(10, min(args.steps, 100))
+    t_fwd = timed(lambda k: ctx.transform_fwd_dev(d_in[k, 0], d_in[k, 1], d_in[k, 2], W, H, B, gray, d_coefs[k], stream=sp), it)
+    t_ent = timed(lambda k: ctx.entropy_encode_dev(d_coefs[k], W, H, B, gray, d_scan[k], slot, d_nbytes[k], None, stream=sp), it)
+    t_dent = timed(lambda k: ctx.entropy_decode_dev(d_scan[k], slot, h_nbytes[k], B, frame, d_coefs[k], d_status[k], stream=sp), it)
+    t_inv = timed(lambda k: ctx.transform_inv_dev(d_coefs[k], frame, B, gray, d_out[k, 0], d_out[k, 1], d_out[k, 2], plane_len, stream=sp), it)
+    sampler.mark = None
+    peak, peak_src = measured_peak()
+    bpp = 5.0 if gray else 6.0     # 3 B/px RGB in + 3 B/px int16 coefficients out (gray: chroma coefficients constant)
+    dom = ("k_fwd_transform", t_fwd) if t_fwd >= t_inv else ("k_inv_transform", t_inv)
+    alg_bytes = bpp * B * npx
+    achieved = alg_bytes / (dom[1] * 1e-3) / 1e9
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = prof.get(args.workload, {}).get(dom[0])
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "ms_per_launch": dom[1]}
+    scan_bytes = float(np.mean([x.sum() for x in h_nbytes if x is not None]))
+    stages = {"fwd_transform_ms": t_fwd, "entropy_encode_ms": t_ent, "entropy_decode_ms": t_dent, "inv_transform_ms": t_inv,
+              "fwd_transform_GBs": bpp * B * npx / t_fwd / 1e6, "inv_transform_GBs": bpp * B * npx / t_inv / 1e6,
+              "entropy_encode_Gbit_s": scan_bytes * 8 / t_ent / 1e6, "entropy_decode_Gbit_s": scan_bytes * 8 / t_dent / 1e6,
+              "scan_bytes_per_step": scan_bytes, "bits_per_pixel": scan_bytes * 8 / (B * npx),
+              "encode_MPix_s": B * npx / (t_fwd + t_ent) / 1e3, "decode_MPix_s": B * npx / (t_dent + t_inv) / 1e3}
+
+    # ---- e2e: host buffers through jpezyb200_encode / jpezyb200_decode, pinned memory, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        nh = max(2, min(ring, 4))
+        hin = [[torch.empty(npx, dtype=torch.uint8).pin_memory() for _ in range(3)] for _ in range(nh)]
+        for k in range(nh):
+            for c in range(3):
+                hin[k][c].copy_(d_in[k % ring, c, 0].reshape(-1).cpu())
+        hscan = torch.empty(max(npx * 3, 10240), dtype=torch.uint8).pin_memory()
+        hout = [torch.empty(plane_len, dtype=torch.uint8).pin_memory() for _ in range(3)]
+        L = ctx.lib
+        import ctypes as C
+        nbytes_c, nbits_c = C.c_size_t(0), C.c_uint64(0)
+
+        def e2e_step(k):
+            tot = 0
+            for _ in range(B):     # the host API is per image, as the reference's encoder/decoder objects are
+                ctx._chk(L.jpezyb200_encode(ctx.h, hin[k][0].data_ptr(), hin[k][1].data_ptr(), hin[k][2].data_ptr(), W, H, int(gray),
+                                            hscan.data_ptr(), hscan.numel(), C.byref(nbytes_c), C.byref(nbits_c)))
+                ctx._chk(L.jpezyb200_decode(ctx.h, hscan.data_ptr(), nbytes_c.value, C.byref(frame), int(gray), hout[0].data_ptr(),
+                                            hout[1].data_ptr(), hout[2].data_ptr(), plane_len))
+                tot += nbytes_c.value
+            return tot
+        for i in range(3):
+            e2e_step(i % nh)
+        n_e2e = max(3, min(args.steps, 20))
+        barrier()
+        t0 = time.perf_counter()
+        sb = 0
+        for i in range(n_e2e):
+            sb += e2e_step(i % nh)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        sb /= n_e2e
+        e2e = {"value": world * B * npx * n_e2e / dt / 1e6, "unit": "MPix/s", "h2d_bytes_per_step": int(3 * npx * B + sb),
+               "d2h_bytes_per_step": int(sb + 3 * plane_len * B), "steps": n_e2e,
+               "api": "jpezyb200_encode + jpezyb200_decode (host pointers, pinned)"}
+
+    sampler.stop_flag = True
+    clocks = sampler.summary()
+
+    # ---- CPU baseline: the oracle port on the host cores, rank 0 at N=1 only, bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle as orc
+        orc.build()
+        o = orc.Oracle("shipped")
+        rows = min(H, 1024)
+        r, g, b = (d_in[0, c, 0, :rows].cpu().numpy() for c in range(3))
+        wall1, te1, td1 = o.time_roundtrip(r, g, b, W, rows, gray, 1, 1)
+        cores = os.cpu_count() or 1
+        wallc, _, _ = o.time_roundtrip(r, g, b, W, rows, gray, 1, cores)
+        px = float(W) * rows
+        cpu = {"value": px / wall1 / 1e6, "unit": "MPix/s", "cores": 1, "kind": "port",
+               "sample": "%dx%d band (first %d rows) of one workload frame, 1 round trip, encode()+decode() in memory, PPM I/O excluded" % (W, rows, rows),
+               "encode_MPix_s": px / te1 / 1e6, "decode_MPix_s": px / td1 / 1e6,
+               "all_cores": {"cores": cores, "value": px * cores / wallc / 1e6, "how": "one instance per core (threads)"}}
+
+    if rank == 0:
+        line = {"metric": "encode+decode MPix/s", "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["name"], "width": W, "height": H, "batch_per_gpu": B, "gray": gray,
+                           "family": "S-photo" if args.family == 0 else "S-noise",
+                           "l2": "ring of %d distinct input/output frame sets (%.0f MB) rotated between steps; > 126 MB L2" % (
+                               ring, ring * (in_bytes + out_bytes) / 1e6),
+                           "sharding": "by image, no data-path collective"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "stages": stages}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
