@@ -99,11 +99,34 @@ int jpezyb200_ctx_create(int device, jpezyb200_ctx** out)
         }
         h.inv_sqrt2_ref = kInvSqrt2Ref;
         JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(cC, &h, sizeof h));
+        {
+            // constants of the FP32 AAN path: K folds the AAN scale factors, the /8 and 1/q; G is the guard band
+            // (1.25 x worst-case flowgraph error + the rounding of w itself) in w units; T the "quantises to 0" test
+            QuantConst qc{};
+            double aan[8];
+            aan[0] = 1.0;
+            for (int k = 1; k < 8; ++k) aan[k] = std::cos(k * 3.14159265358979323846 / 16) * std::sqrt(2.0);
+            for (int c = 0; c < 2; ++c)
+                for (int i = 0; i < 8; ++i)
+                    for (int j = 0; j < 8; ++j) {
+                        const double q = c ? kQuantChroma[i * 8 + j] : kQuantLuma[i * 8 + j];
+                        const double K = 1.0 / (8.0 * aan[i] * aan[j] * q);
+                        const double Gd = (1.25 * kAanErrBound[i * 8 + j] + 5e-4) / q;
+                        qc.K[c][i * 8 + j] = float(K);
+                        qc.G[c][i * 8 + j] = float(Gd);
+                        qc.T[c][i * 8 + j] = float((1.0 - 2.0 * Gd) / K);
+                    }
+            JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(cQ, &qc, sizeof qc));
+        }
         HuffEncLut lut[2];
         build_enc_lut(kDcLuma, kAcLuma, &lut[0]);
         build_enc_lut(kDcChroma, kAcChroma, &lut[1]);
         JZ_CUDA_TRY(ctx, cudaMalloc(&ctx->d_enc_lut, sizeof lut));
         JZ_CUDA_TRY(ctx, cudaMemcpy(ctx->d_enc_lut, lut, sizeof lut, cudaMemcpyHostToDevice));
+        JZ_CUDA_TRY(ctx, cudaMalloc(&ctx->d_y_exact, 65536));
+        k_build_y_exact<<<256, 256, 0, ctx->stream>>>(ctx->d_y_exact);
+        JZ_CUDA_TRY(ctx, cudaGetLastError());
+        JZ_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         JZ_CUDA_TRY(ctx, cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
         JZ_CUDA_TRY(ctx, cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)));
         return JPEZYB200_OK;
@@ -130,6 +153,7 @@ void jpezyb200_ctx_destroy(jpezyb200_ctx* ctx)
     if (ctx->d_enc_lut) cudaFree(ctx->d_enc_lut);
     if (ctx->d_dec_lut) cudaFree(ctx->d_dec_lut);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_y_exact) cudaFree(ctx->d_y_exact);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -186,8 +210,14 @@ static int launch_fwd(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g
     p.row0 = 0, p.y_origin = 0;
     p.gray = gray;
     p.guard_counter = ctx->d_counters + 0;
-    dim3 grid((p.HU + kMcuPerCta - 1) / kMcuPerCta, p.VU, nimg);
-    k_fwd_transform_f64<<<grid, kFwdThreads, 0, st>>>(p);
+    p.y_exact = ctx->d_y_exact;
+    if (ctx->transform_variant == 1) {
+        dim3 grid((p.HU + kMcuPerCta - 1) / kMcuPerCta, p.VU, nimg);
+        k_fwd_transform_f64<<<grid, kFwdThreads, 0, st>>>(p);
+    } else {
+        dim3 grid((p.HU + kTileMcu - 1) / kTileMcu, p.VU, nimg);
+        k_fwd_transform<<<grid, 256, 0, st>>>(p);
+    }
     ++ctx->launches;
     JZ_CUDA_TRY(ctx, cudaGetLastError());
     return JPEZYB200_OK;

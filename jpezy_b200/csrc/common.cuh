@@ -70,6 +70,7 @@ struct jpezyb200_ctx {
 
     // counters on the device: [0] guard_fwd, [1] guard_inv, [2] sync rounds, [3] scratch
     unsigned long long* d_counters = nullptr;
+    int8_t* d_y_exact = nullptr;   // 64 KiB table of the exact luma cases (enc_transform.cuh)
 
     // scratch
     jz_devbuf coefs, blk_off, tile_sum, tile_base, img_bits, ustream, ff_sum, ff_base, planes_in, planes_out, scan_io, sizes_io;

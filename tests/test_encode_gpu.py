@@ -48,14 +48,24 @@ def test_coefficients_bit_exact(ctx, oracle, W, H, family, gray):
 
 
 def test_guard_path_is_exercised(ctx, oracle):
-    # flat gray tiles: every DC sits on a multiple of its quantiser whenever 8p % 16 == 0 -> the exact-order
-    # recompute decides (hard part 1: DC = 8p -+ 1 ulp)
+    # flat gray tiles: every DC sits on a multiple of its quantiser whenever 8p % 16 == 0 -> the reference's FP64
+    # rounding decides (hard part 1: DC = 8p -+ 1 ulp); the DC path evaluates ((S*c)*c)/4 as the reference does
     W, H = 256, 64
-    before = ctx.stat(capi.STAT_GUARD_FWD)
     r, g, b = planes(2, W, H)
-    got = gpu_coefs(ctx, r, g, b, W, H)[0]
-    assert (got == oracle.coefs(r, g, b, W, H)).all()
-    assert ctx.stat(capi.STAT_GUARD_FWD) > before
+    assert (gpu_coefs(ctx, r, g, b, W, H)[0] == oracle.coefs(r, g, b, W, H)).all()
+    # an AC coefficient exactly on a boundary: columns a,b,b,a,a,b,b,a give F(0,4) = 4(a-b); 4*6 = 24 = q(0,4)
+    found = False
+    for base in range(20, 200, 7):
+        row = np.array([base + 6, base, base, base + 6, base + 6, base, base, base + 6] * 4, dtype=np.uint8)
+        v = np.tile(row, (16, 1))
+        c, raw = oracle.coefs(v, v, v, 32, 16, want_raw=True)
+        if abs(abs(raw[0, 0, 4]) - 24.0) < 1e-9:
+            found = True
+            before = ctx.stat(capi.STAT_GUARD_FWD)
+            assert (gpu_coefs(ctx, v, v, v, 32, 16)[0] == c).all()
+            assert ctx.stat(capi.STAT_GUARD_FWD) > before, "tier-3 (exact operation order) path was not taken"
+            break
+    assert found
 
 
 def test_exhaustive_colour_conversion(ctx, oracle):
