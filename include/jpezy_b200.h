@@ -39,7 +39,11 @@ enum {
                                    returns an empty optional, src/decoder/jpezy_decoder.hpp:109-114) */
     JPEZYB200_ENODEVICE = 6,    /* no CUDA device: there is no CPU path                            */
     JPEZYB200_ENOMEM = 7,
-    JPEZYB200_EUNSUPPORTED = 8  /* frame layout outside what the device decoder handles            */
+    JPEZYB200_EUNSUPPORTED = 8, /* frame layout outside what the device decoder handles            */
+    JPEZYB200_EAGAIN = 9        /* *_dev decode only (reported per image in d_status): the parallel
+                                   Huffman decoder did not reach its fixed point within the enqueued
+                                   rounds; decode again with JPEZYB200_OPT_SYNC_ROUNDS = 0.  The
+                                   host-pointer entry point jpezyb200_decode does that by itself.   */
 };
 
 typedef struct jpezyb200_ctx jpezyb200_ctx;
@@ -57,9 +61,13 @@ enum {
     JPEZYB200_OPT_PAD_ONES = 1,   /* fill bits of the last scan byte: 1 (default, T.81 F.1.2.3) or 0.
                                      Replaces the padding decision inside srook::io::jpeg::bofstream
                                      (call site src/encoder/jpezy_writer.hpp:101-105). */
-    JPEZYB200_OPT_TRANSFORM = 2   /* forward/inverse transform kernel variant: 0 = fast path with
+    JPEZYB200_OPT_TRANSFORM = 2,  /* forward/inverse transform kernel variant: 0 = fast path with
                                      guard band + exact recompute (default), 1 = FP64 separable
                                      (validation build)                                           */
+    JPEZYB200_OPT_SYNC_ROUNDS = 3 /* self-synchronisation launches enqueued after the first one by the
+                                     decoder: n > 0 = exactly n, no host round trip (default 4; two are
+                                     needed on ordinary streams, later ones return at once); 0 = the
+                                     host polls a device flag after every launch until the fixed point */
 };
 JPEZYB200_API int jpezyb200_set_option(jpezyb200_ctx* ctx, int option, int64_t value);
 

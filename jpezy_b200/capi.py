@@ -6,8 +6,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-OK, EINVAL, ECAPACITY, ECUDA, ENCCL, ECORRUPT, ENODEVICE, ENOMEM, EUNSUPPORTED = range(9)
-OPT_PAD_ONES, OPT_TRANSFORM = 1, 2
+OK, EINVAL, ECAPACITY, ECUDA, ENCCL, ECORRUPT, ENODEVICE, ENOMEM, EUNSUPPORTED, EAGAIN = range(10)
+OPT_PAD_ONES, OPT_TRANSFORM, OPT_SYNC_ROUNDS = 1, 2, 3
 STAT_KERNEL_LAUNCHES, STAT_GUARD_FWD, STAT_GUARD_INV, STAT_SYNC_ROUNDS = 1, 2, 3, 4
 
 EXPORTS = [

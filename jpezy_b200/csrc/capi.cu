@@ -66,6 +66,7 @@ const char* jpezyb200_strerror(int code)
     case JPEZYB200_ENODEVICE: return "no CUDA device (libjpezy_b200 has no CPU path)";
     case JPEZYB200_ENOMEM: return "out of memory";
     case JPEZYB200_EUNSUPPORTED: return "unsupported frame layout";
+    case JPEZYB200_EAGAIN: return "parallel Huffman decoder needs more synchronisation rounds";
     default: return "unknown error";
     }
 }
@@ -147,7 +148,7 @@ void jpezyb200_ctx_destroy(jpezyb200_ctx* ctx)
     jz_devbuf* bufs[] = {&ctx->coefs, &ctx->blk_off, &ctx->tile_sum, &ctx->tile_base, &ctx->img_bits, &ctx->ustream,
                          &ctx->ff_sum, &ctx->ff_base, &ctx->planes_in, &ctx->planes_out, &ctx->scan_io, &ctx->sizes_io,
                          &ctx->dec_scanbytes, &ctx->dec_chunk_cnt, &ctx->dec_chunk_base, &ctx->dec_ubytes, &ctx->dec_state,
-                         &ctx->dec_dirty, &ctx->dec_subblk, &ctx->dec_dc, &ctx->dec_status};
+                         &ctx->dec_dirty, &ctx->dec_subblk, &ctx->dec_dc, &ctx->dec_status, &ctx->dec_changed};
     for (jz_devbuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_enc_lut) cudaFree(ctx->d_enc_lut);
@@ -165,6 +166,10 @@ int jpezyb200_set_option(jpezyb200_ctx* ctx, int option, int64_t value)
     switch (option) {
     case JPEZYB200_OPT_PAD_ONES: ctx->pad_ones = value ? 1 : 0; return JPEZYB200_OK;
     case JPEZYB200_OPT_TRANSFORM: ctx->transform_variant = int(value); return JPEZYB200_OK;
+    case JPEZYB200_OPT_SYNC_ROUNDS:
+        if (value < 0 || value > 64) return ctx->fail(JPEZYB200_EINVAL, "sync rounds must be in 0..64");
+        ctx->sync_rounds = int(value);
+        return JPEZYB200_OK;
     default: return ctx->fail(JPEZYB200_EINVAL, "unknown option");
     }
 }

@@ -60,7 +60,9 @@ struct jpezyb200_ctx {
     std::string err;
     int pad_ones = 1;
     int transform_variant = 0;
+    int sync_rounds = 4;
     uint64_t launches = 0;
+    bool inv_attr_set = false;
 
     // device-resident tables
     jz::HuffEncLut* d_enc_lut = nullptr;  // [2]
@@ -74,7 +76,7 @@ struct jpezyb200_ctx {
 
     // scratch
     jz_devbuf coefs, blk_off, tile_sum, tile_base, img_bits, ustream, ff_sum, ff_base, planes_in, planes_out, scan_io, sizes_io;
-    jz_devbuf dec_scanbytes, dec_chunk_cnt, dec_chunk_base, dec_ubytes, dec_state, dec_dirty, dec_subblk, dec_dc, dec_status;
+    jz_devbuf dec_scanbytes, dec_chunk_cnt, dec_chunk_base, dec_ubytes, dec_state, dec_dirty, dec_subblk, dec_dc, dec_status, dec_changed;
     void* h_pinned = nullptr;
     size_t h_pinned_cap = 0;
 

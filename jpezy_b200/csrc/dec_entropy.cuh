@@ -27,7 +27,7 @@ constexpr int kLutBits = 10;
 
 // compact canonical decoder table for one DHT table, built on the host
 struct HuffDecTab {
-    uint16_t fast[1 << kLutBits];  // peek kLutBits bits -> (len << 8) | symbol, 0 = longer than kLutBits / invalid
+    uint16_t fast[1 << kLutBits];  // peek kLutBits bits -> len | size << 5 | run << 9, 0 = longer than kLutBits / invalid
     int32_t maxcode[18];           // maxcode[len] (left-aligned compare uses plain codes), -1 = none
     int32_t valptr[17];            // index into vals of the first code of this length minus its code
     uint8_t vals[256];
@@ -51,12 +51,14 @@ struct DecParams {
     // synchronisation
     uint32_t sub_bits;        // subsequence length in bits (power of two >= 128)
     uint32_t nsub;            // subsequences per image (capacity)
-    uint32_t* state_a;        // [nimg][nsub] packed end states, double buffered
+    uint32_t* sub_state;      // [nimg][nsub] packed end state of every subsequence
+    uint32_t* state_a;        // [nimg][ncta] CTA tail states, double buffered across launches
     uint32_t* state_b;
-    uint8_t* dirty_a;         // [nimg][nsub]
-    uint8_t* dirty_b;
     uint32_t* sub_blk;        // [nimg][nsub] exclusive prefix of block counts
-    unsigned long long* changed;   // device flag: number of end states that changed this round
+    unsigned long long* changed;   // [rounds + 1] number of end states that changed in launch k (k >= 1); zeroed per call
+    uint32_t rounds;          // launches 1..rounds of k_sync_decode are enqueued after launch 0
+    uint32_t rounds_host;     // launches the host-driven loop needed (rounds == 0)
+    unsigned long long* rounds_stat;   // receives the number of launches that did work
     // tables: [0]=DC sel by comp class 0, [1]=DC class 1, [2]=AC class 0, [3]=AC class 1
     const HuffDecTab* tabs;
     // output
@@ -75,75 +77,84 @@ __device__ __forceinline__ uint32_t pack_state(uint32_t over, uint32_t b, uint32
 }
 constexpr uint32_t kStateSyncMask = (1u << 15) - 1u;   // (overshoot, b, z)
 
-// ---- bit reader over the un-stuffed stream (big-endian bit order) -------------------------------
-struct BitPeek {
-    const uint8_t* base;
-    __device__ __forceinline__ uint32_t peek32(uint64_t p) const
+// ---- bit reader over the un-stuffed stream (big-endian bit order), 64-bit register buffer ------------
+struct BitBuf {
+    const uint32_t* w;   // next word to load
+    uint64_t buf;        // left-aligned
+    int n;               // valid bits in buf
+    uint64_t pos;        // absolute bit position of the first bit of buf
+    __device__ __forceinline__ void init(const uint8_t* base, uint64_t p)
     {
-        // 32 bits starting at bit p (stream has >= 8 bytes of slack after the data)
-        const uint64_t byte = p >> 3;
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(base + (byte & ~uint64_t(3)));
+        w = reinterpret_cast<const uint32_t*>(base) + (p >> 5);
         const uint32_t a = __byte_perm(__ldg(w), 0, 0x0123), b = __byte_perm(__ldg(w + 1), 0, 0x0123);
+        w += 2;
         const uint32_t sh = uint32_t(p & 31u);
-        return __funnelshift_l(b, a, sh);
+        buf = ((uint64_t(a) << 32) | b) << sh;
+        n = 64 - int(sh);
+        pos = p;
     }
+    __device__ __forceinline__ void refill()   // guarantees n >= 32
+    {
+        if (n < 32) {
+            buf |= uint64_t(__byte_perm(__ldg(w++), 0, 0x0123)) << (32 - n);
+            n += 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek32() const { return uint32_t(buf >> 32); }
+    __device__ __forceinline__ void skip(int k) { buf <<= k; n -= k; pos += k; }
 };
 
 __device__ __forceinline__ uint32_t huff_lookup(const HuffDecTab* __restrict__ t, const uint16_t* __restrict__ s_fast, uint32_t bits32)
 {
-    // returns (len << 8) | symbol, len = 0 when no code matches
+    // returns len | size << 5 | run << 9 (size = low nibble of the symbol, run = high nibble), 0 when no code matches
     const uint32_t e = s_fast[bits32 >> (32 - kLutBits)];
     if (e) return e;
 #pragma unroll 1
     for (int len = kLutBits + 1; len <= 16; ++len) {
         const int32_t code = int32_t(bits32 >> (32 - len));
-        if (code <= t->maxcode[len]) return (uint32_t(len) << 8) | t->vals[(code + t->valptr[len]) & 255];
+        if (code <= t->maxcode[len]) {
+            const uint32_t sym = t->vals[(code + t->valptr[len]) & 255];
+            return uint32_t(len) | ((sym & 15u) << 5) | ((sym >> 4) << 9);
+        }
     }
     return 0;
 }
 
-// Decode from (p, b, z) until p >= end or the image's blocks are exhausted.  Sink receives
-// (block_ordinal_within_this_call, zz_index, value) for every coefficient with a value field.
+// Decode from (br.pos, b, z) until br.pos >= end (or >= limit).  With kWrite the coefficients that carry a value
+// field are stored (the buffer is pre-zeroed), block ordinals start at blk.
 template <bool kWrite>
-__device__ __forceinline__ void decode_span(const BitPeek& br, uint64_t& p, uint32_t& b, uint32_t& z, uint32_t& nblocks,
-                                            const uint64_t end, const uint64_t limit, const HuffDecTab* __restrict__ tabs,
+__device__ __forceinline__ void decode_span(BitBuf& br, uint32_t& b, uint32_t& z, uint32_t& nblocks, const uint64_t end,
+                                            const uint64_t limit, const HuffDecTab* __restrict__ tabs,
                                             const uint16_t (*s_fast)[1 << kLutBits], int16_t* __restrict__ out, uint64_t blk,
                                             const uint64_t nblk, int* corrupt)
 {
-    while (p < end && p < limit) {
-        const int cls = b >= 4;
-        const int ti = (z == 0 ? 0 : 2) + cls;
-        const uint32_t w = br.peek32(p);
+    const uint64_t stop = end < limit ? end : limit;
+    while (br.pos < stop) {
+        br.refill();
+        const int ti = (z == 0 ? 0 : 2) + (b >= 4 ? 1 : 0);
+        const uint32_t w = br.peek32();
         const uint32_t e = huff_lookup(tabs + ti, s_fast[ti], w);
-        uint32_t len = e >> 8, sym = e & 255u;
-        if (len == 0) {            // no such code: only legal while speculating
+        if (e == 0) {              // no such code: only legal while speculating
             if (kWrite && corrupt) *corrupt = 1;
-            len = 1, sym = 0xffu;  // skip a bit, keep the state
-            p += 1;
+            br.skip(1);
             continue;
         }
-        const uint32_t s = (z == 0) ? (sym & 15u) : (sym & 15u);
-        const uint32_t run = (z == 0) ? 0u : (sym >> 4);
-        if (z != 0 && sym == 0) {  // EOB
-            p += len;
+        const uint32_t len = e & 31u, s = (e >> 5) & 15u;
+        const uint32_t run = (z == 0) ? 0u : (e >> 9);
+        br.skip(int(len + s));     // len + s <= 31 and the buffer holds >= 32 bits
+        if (z != 0 && (e >> 5) == 0) {   // EOB (run = size = 0)
             z = 64;
         } else {
-            // value bits follow the code; len + s <= 32 holds for s <= 16
-            uint32_t vbits = 0;
-            if (s) {
-                const uint32_t w2 = (len + s <= 32) ? (w << len) : br.peek32(p + len);
-                vbits = w2 >> (32 - s);
-            }
-            p += len + s;
             z += run;
             if (z > 63) {          // run past the end of the block (src/decoder/jpezy_decoder.hpp:619)
                 if (kWrite && corrupt) *corrupt = 1;
                 z = 64;
             } else {
-                if (kWrite && blk < nblk) {
+                if (kWrite && s && blk < nblk) {
+                    const uint32_t vbits = (w << len) >> (32 - s);
                     int v = int(vbits);
-                    if (s && !(vbits & (1u << (s - 1)))) v -= (1 << s) - 1;
-                    if (s) out[blk * 64 + z] = int16_t(v);
+                    if (!(vbits & (1u << (s - 1)))) v -= (1 << s) - 1;
+                    out[blk * 64 + z] = int16_t(v);
                 }
                 z += 1;
             }
@@ -270,102 +281,156 @@ __global__ void __launch_bounds__(kDecThreads) k_unstuff_write(const DecParams p
     }
 }
 
-// ---- D1a: speculative decode / synchronisation rounds -------------------------------------------------
-// round 0: every subsequence starts at its own first bit in state (b=0, z=0).
-// round k: subsequence i restarts from the end state of subsequence i-1 when that changed.
-__global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, const int round)
+// ---- D1a: speculative decode + synchronisation --------------------------------------------------------
+// One CTA owns kDecThreads consecutive subsequences.  Launch 0: every thread decodes its subsequence from the
+// guessed state (b = 0, z = 0); then the CTA iterates in shared memory: a thread whose predecessor's end state
+// changed re-decodes from it, until nothing changes inside the CTA.  Only the first thread of a CTA depends on
+// another CTA (the previous CTA's last end state, `tail`); later launches re-seed it from the previous launch's
+// tails and re-propagate.  `changed` counts the end states that changed during a launch; 0 = global fixed point.
+__global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, const int launch, const int host_poll)
 {
     __shared__ uint16_t s_fast[4][1 << kLutBits];
+    __shared__ uint32_t s_state[kDecThreads];
+    __shared__ uint8_t s_chg[2][kDecThreads];
+    // launches are enqueued without host round trips: once a launch saw no change (a global fixed point), the
+    // later ones return immediately (changed[] stays 0 for them, so the zero propagates to changed[rounds])
+    // (host_poll: the host reads changed[1] after every launch instead)
+    if (!host_poll && launch >= 2 && p.changed[launch - 1] == 0) return;
     load_dec_tabs(p.tabs, s_fast);
-    __syncthreads();
     const size_t img = blockIdx.y;
     const uint64_t total_bits = p.ubytes[img] * 8;
-    const uint32_t i = blockIdx.x * kDecThreads + threadIdx.x;
+    const int t = threadIdx.x;
+    const uint32_t i = blockIdx.x * kDecThreads + t;
     const uint64_t start = uint64_t(i) * p.sub_bits;
-    if (start >= total_bits || i >= p.nsub) return;
-    const uint32_t* sin = (round & 1) ? p.state_a : p.state_b;   // round 0 writes a, round 1 reads a writes b, ...
-    uint32_t* sout = (round & 1) ? p.state_b : p.state_a;
-    const uint8_t* din = (round & 1) ? p.dirty_a : p.dirty_b;
-    uint8_t* dout = (round & 1) ? p.dirty_b : p.dirty_a;
-    const size_t si = img * p.nsub + i;
+    const bool valid = start < total_bits && i < p.nsub;
     const uint64_t end = start + p.sub_bits;
-    BitPeek br{p.ustream + img * p.uslot};
-    uint64_t pos;
-    uint32_t b, z, n = 0;
-    if (round == 0) {
-        pos = start, b = 0, z = 0;
-    } else {
-        if (i == 0 || !din[si - 1]) {   // predecessor unchanged: keep my end state
-            sout[si] = sin[si];
-            dout[si] = 0;
-            return;
+    const size_t si = img * p.nsub + i;
+    const uint8_t* base = p.ustream + img * p.uslot;
+    const uint32_t ncta = gridDim.x;
+    const uint32_t* tail_in = (launch & 1) ? p.state_b : p.state_a;     // [nimg][ncta] tails of the previous launch
+    uint32_t* tail_out = (launch & 1) ? p.state_a : p.state_b;
+    __syncthreads();
+
+    uint32_t st = 0;
+    bool chg = false;
+    if (valid) {
+        if (launch == 0) {
+            BitBuf br;
+            br.init(base, start);
+            uint32_t b = 0, z = 0, n = 0;
+            decode_span<false>(br, b, z, n, end, total_bits, p.tabs, s_fast, nullptr, 0, 0, nullptr);
+            st = pack_state(uint32_t(br.pos > end ? br.pos - end : 0), b, z, n);
+            chg = true;
+        } else {
+            st = p.sub_state[si];
+            if (t == 0 && blockIdx.x > 0) {
+                const uint32_t ps = tail_in[img * ncta + blockIdx.x - 1];
+                BitBuf br;
+                br.init(base, start + (ps & 63u));
+                uint32_t b = (ps >> 6) & 7u, z = (ps >> 9) & 63u, n = 0;
+                decode_span<false>(br, b, z, n, end, total_bits, p.tabs, s_fast, nullptr, 0, 0, nullptr);
+                const uint32_t ns = pack_state(uint32_t(br.pos > end ? br.pos - end : 0), b, z, n);
+                chg = ((ns ^ st) & kStateSyncMask) != 0;
+                st = ns;
+            }
         }
-        const uint32_t ps = sin[si - 1];
-        pos = start + (ps & 63u), b = (ps >> 6) & 7u, z = (ps >> 9) & 63u;
     }
-    decode_span<false>(br, pos, b, z, n, end, total_bits, p.tabs, s_fast, nullptr, 0, 0, nullptr);
-    const uint64_t over = pos > end ? pos - end : 0;
-    const uint32_t st = pack_state(uint32_t(over), b, z, n);
-    sout[si] = st;
-    if (round == 0) {
-        dout[si] = 1;
-    } else {
-        const bool ch = ((st ^ sin[si]) & kStateSyncMask) != 0;
-        dout[si] = ch ? 1 : 0;
-        if (ch) atomicAdd(p.changed, 1ull);
+    s_state[t] = st;
+    s_chg[0][t] = chg ? 1 : 0;
+    uint32_t nchanged = (launch > 0 && chg) ? 1u : 0u;
+    __syncthreads();
+    for (int it = 0; it < 4 * kDecThreads; ++it) {
+        const bool redo = valid && t > 0 && s_chg[it & 1][t - 1];
+        const uint32_t ps = redo ? s_state[t - 1] : 0u;
+        bool c2 = false;
+        if (redo) {
+            BitBuf br;
+            br.init(base, start + (ps & 63u));
+            uint32_t b = (ps >> 6) & 7u, z = (ps >> 9) & 63u, n = 0;
+            decode_span<false>(br, b, z, n, end, total_bits, p.tabs, s_fast, nullptr, 0, 0, nullptr);
+            const uint32_t ns = pack_state(uint32_t(br.pos > end ? br.pos - end : 0), b, z, n);
+            c2 = ((ns ^ st) & kStateSyncMask) != 0;
+            st = ns;
+        }
+        __syncthreads();                 // all reads of s_state[t-1] are done
+        if (redo) s_state[t] = st;
+        s_chg[(it + 1) & 1][t] = c2 ? 1 : 0;
+        if (c2) ++nchanged;
+        if (!__syncthreads_or(c2 ? 1 : 0)) break;
     }
+    if (valid) p.sub_state[si] = st;
+    // the CTA's last valid subsequence is the seed of the next CTA
+    const uint64_t last_start = uint64_t(blockIdx.x * kDecThreads + kDecThreads - 1) * p.sub_bits;
+    const bool is_tail = valid && (t == kDecThreads - 1 || start + p.sub_bits >= total_bits || i + 1 >= p.nsub);
+    (void)last_start;
+    if (is_tail) tail_out[img * ncta + blockIdx.x] = st;
+    if (launch > 0 && nchanged) atomicAdd(p.changed + (host_poll ? 1 : launch), (unsigned long long)nchanged);
+    // blocks completed inside this CTA's subsequences (input of the block-index scan)
+    uint32_t total;
+    cta_scan_excl(valid ? (st >> 15) & 4095u : 0u, reinterpret_cast<uint32_t*>(s_state), &total);
+    if (t == 0) p.sub_blk[img * ncta + blockIdx.x] = total;
 }
 
-// block counts of the converged states -> sub_blk (exclusive), and per-image status
-__global__ void __launch_bounds__(1024) k_scan_blocks(const DecParams p, const int final_round)
+// exclusive scan of the per-CTA block counts (in place) and per-image status
+__global__ void __launch_bounds__(1024) k_scan_blocks(const DecParams p, const uint32_t ncta)
 {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     const size_t img = blockIdx.x;
-    const uint32_t* st = (final_round & 1) ? p.state_b : p.state_a;   // buffer written by the last round
     const uint64_t total_bits = p.ubytes[img] * 8;
-    const uint32_t n = uint32_t(min(uint64_t(p.nsub), (total_bits + p.sub_bits - 1) / p.sub_bits));
+    const uint32_t nsub = uint32_t(min(uint64_t(p.nsub), (total_bits + p.sub_bits - 1) / p.sub_bits));
+    const uint32_t n = (nsub + kDecThreads - 1) / kDecThreads;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     for (uint32_t c0 = 0; c0 < n; c0 += 1024) {
         const uint32_t c = c0 + threadIdx.x;
-        const uint32_t v = c < n ? (st[img * p.nsub + c] >> 15) & 4095u : 0u;
+        const uint32_t v = c < n ? p.sub_blk[img * ncta + c] : 0u;
         uint32_t total;
         const uint32_t off = cta_scan_excl(v, s_warp, &total);
         const uint32_t carry = s_carry;
-        if (c < n) p.sub_blk[img * p.nsub + c] = carry + off;
+        if (c < n) p.sub_blk[img * ncta + c] = carry + off;
         __syncthreads();
         if (threadIdx.x == 0) s_carry = carry + total;
         __syncthreads();
     }
-    if (threadIdx.x == 0 && p.status) p.status[img] = s_carry >= p.nblk ? 0 : JPEZYB200_ECORRUPT;
+    if (threadIdx.x == 0) {
+        // not a fixed point after the enqueued launches: the caller has to run the host-driven loop (JPEZYB200_EAGAIN)
+        const bool converged = p.rounds == 0 || p.changed[p.rounds] == 0;
+        if (p.status) p.status[img] = !converged ? JPEZYB200_EAGAIN : (s_carry >= p.nblk ? 0 : JPEZYB200_ECORRUPT);
+        if (img == 0) {
+            unsigned long long n = 1 + p.rounds_host;
+            for (uint32_t k = 1; k <= p.rounds; ++k) n += (k == 1 || p.changed[k - 1] != 0) ? 1ull : 0ull;
+            *p.rounds_stat = n;
+        }
+    }
 }
 
 // ---- D1c: final pass, writes the non-zero coefficients (buffer pre-zeroed) ------------------------------
-__global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p, const int final_round)
+__global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p)
 {
     __shared__ uint16_t s_fast[4][1 << kLutBits];
+    __shared__ uint32_t s_warp[kDecThreads / 32];
     load_dec_tabs(p.tabs, s_fast);
-    __syncthreads();
     const size_t img = blockIdx.y;
     const uint64_t total_bits = p.ubytes[img] * 8;
     const uint32_t i = blockIdx.x * kDecThreads + threadIdx.x;
     const uint64_t start = uint64_t(i) * p.sub_bits;
-    if (start >= total_bits || i >= p.nsub) return;
-    const uint32_t* st = (final_round & 1) ? p.state_b : p.state_a;
+    const bool valid = start < total_bits && i < p.nsub;
     const size_t si = img * p.nsub + i;
+    const uint32_t mine = valid ? p.sub_state[si] : 0u;
+    uint32_t total;
+    const uint64_t blk = uint64_t(p.sub_blk[img * gridDim.x + blockIdx.x]) + cta_scan_excl((mine >> 15) & 4095u, s_warp, &total);
+    if (!valid || blk >= p.nblk) return;
     uint64_t pos = start;
     uint32_t b = 0, z = 0, n = 0;
     if (i) {
-        const uint32_t ps = st[si - 1];
+        const uint32_t ps = p.sub_state[si - 1];
         pos = start + (ps & 63u), b = (ps >> 6) & 7u, z = (ps >> 9) & 63u;
     }
-    const uint64_t blk = p.sub_blk[si];
-    if (blk >= p.nblk) return;
-    BitPeek br{p.ustream + img * p.uslot};
+    BitBuf br;
+    br.init(p.ustream + img * p.uslot, pos);
     int corrupt = 0;
-    decode_span<true>(br, pos, b, z, n, start + p.sub_bits, total_bits, p.tabs, s_fast, p.coefs + img * p.coef_stride, blk, p.nblk,
-                      &corrupt);
+    decode_span<true>(br, b, z, n, start + p.sub_bits, total_bits, p.tabs, s_fast, p.coefs + img * p.coef_stride, blk, p.nblk, &corrupt);
     if (corrupt && p.status) p.status[img] = JPEZYB200_ECORRUPT;
 }
 

@@ -2,14 +2,19 @@
 //
 // Replaces inverse_quantization (src/decoder/jpezy_decoder.hpp:645-650), inverse_dct (:652-670), the
 // pixel replication of decode_mcu (:519-524) and make_rgb / to_r,g,b / revise_value (:531-578, :672-676).
-// One CTA reconstructs a strip of kMcuPerCta MCUs: dequantise, 8x8 IDCT (separable fast path), chroma
-// replicated 2x2 from shared memory, YCbCr->RGB, planar stores with row stride = image width.
 //
-// Numerics: the reference truncates int(sum/4 + 128) of an FP64 sum, and the exact value is very often
-// an integer (every DC-only block with an even DC*q/8), where the reference's rounding decides.  Samples
-// whose fast-path value is within kGuardInv of an integer are recomputed in the reference's exact
-// operation order over the block's non-zero coefficients (zero terms add +-0 and cannot change the sum).
-// Algorithmic HBM traffic: 3 B/px read (int16 coefficients) + 3 B/px written = 6 B/px.
+// Numerics: the reference truncates int(sum/4 + 128) of an FP64 sum and then truncates the FP64 colour
+// formulas, so results flip on 1-ulp differences when an exact value is an integer -- which is the common
+// case for DC-only blocks and for neutral chroma.  The production kernel computes the IDCT in FP32 (AAN
+// flowgraph) and decides every sample whose value is further than a guard band from an integer; the guard
+// band is the worst-case FP32 error of the flowgraph for that block (sum of |coefficient| * sensitivity,
+// tools/aan_idct_error_bound.py).  Samples inside the band, and whole DC-only blocks, go to a shared-memory
+// queue and are re-evaluated densely in FP64, in the reference's exact operation order when they are within
+// 1e-9 of an integer.  The colour conversion is FP32 with the same kind of argument (the exact values are
+// multiples of 1e-4; R and B can only be integers when the chroma term is exactly 0), falling back to the
+// reference's FP64 expression for the few chroma pairs whose G term is within 7.5e-5 of an integer.
+// Result: decoded samples identical to the reference decoder's.  Algorithmic HBM traffic: 3 B/px read
+// (int16 coefficients) + 3 B/px written = 6 B/px.
 #pragma once
 #include "common.cuh"
 #include "enc_transform.cuh"
@@ -23,8 +28,10 @@ struct InvParams {
     size_t plane_stride;      // bytes between images (= plane_bytes)
     uint32_t W, H, HU, VU;
     int gray;
-    uint16_t qt[3][64];       // per component, natural order
     unsigned long long* guard_counter;
+    uint16_t qt[3][64];       // per component, natural order
+    float M[3][64];           // q * aan_v * aan_u / 8: dequantisation folded with the AAN input scaling
+    float Wg[3][64];          // q * E * 2^-24 * 1.25: guard-band contribution per unit |coefficient|
 };
 
 constexpr double kGuardInv = 1e-6;
@@ -59,6 +66,7 @@ __device__ __forceinline__ uint8_t ref_G(int y, int cb, int cr)
 }
 __device__ __forceinline__ uint8_t ref_B(int y, int cb) { return revise(__dadd_rn(double(y), __dmul_rn(double(cb - 128), 1.7718))); }
 
+// ---- validation build: FP64 separable IDCT ----------------------------------------------------------
 __global__ void __launch_bounds__(kFwdThreads) k_inv_transform_f64(const InvParams p)
 {
     __shared__ int s_dq[kBlkPerCta][64];                 // dequantised, natural order
@@ -72,7 +80,6 @@ __global__ void __launch_bounds__(kFwdThreads) k_inv_transform_f64(const InvPara
     const size_t img = blockIdx.z;
     const uint32_t nvalid = min(uint32_t(kMcuPerCta), p.HU - mx0);
 
-    // ---- load + dequantise (zig-zag -> natural) ----
     const int16_t* src = p.coefs + img * p.coef_stride + (size_t(my) * p.HU + mx0) * 384;
     for (uint32_t e = t; e < kBlkPerCta * 64; e += kFwdThreads) {
         const uint32_t blk = e >> 6, n = e & 63;
@@ -88,8 +95,6 @@ __global__ void __launch_bounds__(kFwdThreads) k_inv_transform_f64(const InvPara
             if (s_dq[t][i]) m |= 1ull << i;
         s_nz[t] = m;
     }
-
-    // ---- IDCT pass 1 (over v): tmp[y][u] = sum_v cv * F[v][u] * cos[v][y] ----
     for (int task = t; task < kBlkPerCta * 8; task += kFwdThreads) {
         const int blk = task >> 3, u = task & 7;
         double col[8];
@@ -104,8 +109,6 @@ __global__ void __launch_bounds__(kFwdThreads) k_inv_transform_f64(const InvPara
         }
     }
     __syncthreads();
-
-    // ---- IDCT pass 2 (over u) + level shift + guard ----
     unsigned long long guard_hits = 0;
     for (int task = t; task < kBlkPerCta * 8; task += kFwdThreads) {
         const int blk = task >> 3, y = task & 7;
@@ -131,7 +134,6 @@ __global__ void __launch_bounds__(kFwdThreads) k_inv_transform_f64(const InvPara
     __syncthreads();
     if (guard_hits) atomicAdd(p.guard_counter, guard_hits);
 
-    // ---- upsample + colour + store ----
     uint8_t* R = p.r + img * p.plane_stride;
     uint8_t* G = p.g + img * p.plane_stride;
     uint8_t* B = p.b + img * p.plane_stride;
@@ -150,6 +152,346 @@ __global__ void __launch_bounds__(kFwdThreads) k_inv_transform_f64(const InvPara
             const int cpos = (ry >> 1) * 8 + ((cx & 15) >> 1);
             const int cb = s_pix[mcu * 6 + 4][cpos], cr = s_pix[mcu * 6 + 5][cpos];
             R[idx] = ref_R(yv, cr), G[idx] = ref_G(yv, cb, cr), B[idx] = ref_B(yv, cb);
+        }
+    }
+}
+
+// =====================================================================================================
+// Production kernel
+// =====================================================================================================
+constexpr int kIYStride = 1040;    // bytes per row of the luma sample tile (512 int16 + 16)
+constexpr int kICStride = 528;     // bytes per row of a chroma sample tile (256 int16 + 16)
+constexpr int kInvSmem = kTileBlk * kOutStride + 16 * kIYStride + 2 * 8 * kICStride + kFixCap * 2 + 16;
+
+// worst-case output error of the FP32 AAN inverse flowgraph per unit of dequantised coefficient, in units of
+// 2^-24 (tools/aan_idct_error_bound.py), natural order, rounded up
+static const float kIdctErrSens[64] = {
+    1.0f, 11.5f, 3.1f, 11.7f, 1.1f, 8.1f, 1.7f, 2.9f,
+    7.9f, 78.4f, 24.7f, 80.6f, 7.9f, 54.0f, 10.4f, 15.8f,
+    2.1f, 21.3f, 6.5f, 21.8f, 2.1f, 14.7f, 2.9f, 4.6f,
+    8.1f, 82.0f, 25.5f, 84.2f, 8.1f, 56.5f, 10.9f, 16.8f,
+    1.1f, 11.5f, 3.1f, 11.7f, 1.1f, 8.1f, 1.7f, 2.9f,
+    5.9f, 60.5f, 18.5f, 62.1f, 5.9f, 41.8f, 8.2f, 12.7f,
+    1.7f, 18.6f, 5.1f, 18.9f, 1.7f, 13.0f, 2.7f, 4.4f,
+    2.6f, 27.9f, 8.0f, 28.5f, 2.6f, 19.4f, 3.9f, 6.3f};
+
+// AAN inverse 1-D DCT on 8 registers (inputs pre-scaled by aan_k, see InvParams::M)
+__device__ __forceinline__ void aan_idct8(float& d0, float& d1, float& d2, float& d3, float& d4, float& d5, float& d6, float& d7)
+{
+    const float t10 = d0 + d4, t11 = d0 - d4;
+    const float t13 = d2 + d6;
+    const float t12 = fmaf(d2 - d6, 1.414213562373095049f, -t13);
+    const float e0 = t10 + t13, e3 = t10 - t13, e1 = t11 + t12, e2 = t11 - t12;
+    const float z13 = d5 + d3, z10 = d5 - d3, z11 = d1 + d7, z12 = d1 - d7;
+    const float o7 = z11 + z13;
+    const float o11 = (z11 - z13) * 1.414213562373095049f;
+    const float z5 = (z10 + z12) * 1.847759065022573512f;
+    const float o10 = fmaf(z12, 1.082392200292393968f, -z5);
+    const float o12 = fmaf(z10, -2.613125929752753055f, z5);
+    const float o6 = o12 - o7;
+    const float o5 = o11 - o6;
+    const float o4 = o10 + o5;
+    d0 = e0 + o7, d7 = e0 - o7;
+    d1 = e1 + o6, d6 = e1 - o6;
+    d2 = e2 + o5, d5 = e2 - o5;
+    d4 = e3 + o4, d3 = e3 - o4;
+}
+
+// dequantise one 16-byte group (8 zig-zag consecutive coefficients) into the natural-order register array
+template <int COMP, int GRP>
+__device__ __forceinline__ void dequant_group(const InvParams& p, const uint4 raw, float (&d)[64], float& gsum)
+{
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+        const int nat = zz_at(GRP * 8 + h);
+        const int c = (h & 1) ? (int(w[h >> 1]) >> 16) : int(short(w[h >> 1] & 0xffffu));
+        const float cf = float(c);
+        d[nat] = cf * p.M[COMP][nat];
+        gsum = fmaf(fabsf(cf), p.Wg[COMP][nat], gsum);
+    }
+}
+
+template <int COMP>
+__device__ __forceinline__ void dequant_block(const InvParams& p, const uint4* __restrict__ src, float (&d)[64], float& gsum, bool& dc_only)
+{
+    uint4 raw[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) raw[g] = src[g];
+    uint32_t ac = (raw[0].x >> 16) | raw[0].y | raw[0].z | raw[0].w;
+#pragma unroll
+    for (int g = 1; g < 8; ++g) ac |= raw[g].x | raw[g].y | raw[g].z | raw[g].w;
+    dc_only = ac == 0;
+    gsum = 2e-5f;
+#pragma unroll
+    for (int k = 0; k < 64; ++k) d[k] = 0.0f;
+    // group 0 always; the other groups only when some lane of the warp has a non-zero coefficient in them
+    dequant_group<COMP, 0>(p, raw[0], d, gsum);
+    if (__any_sync(0xffffffffu, (raw[1].x | raw[1].y | raw[1].z | raw[1].w) != 0)) dequant_group<COMP, 1>(p, raw[1], d, gsum);
+    if (__any_sync(0xffffffffu, (raw[2].x | raw[2].y | raw[2].z | raw[2].w) != 0)) dequant_group<COMP, 2>(p, raw[2], d, gsum);
+    if (__any_sync(0xffffffffu, (raw[3].x | raw[3].y | raw[3].z | raw[3].w) != 0)) dequant_group<COMP, 3>(p, raw[3], d, gsum);
+    if (__any_sync(0xffffffffu, (raw[4].x | raw[4].y | raw[4].z | raw[4].w) != 0)) dequant_group<COMP, 4>(p, raw[4], d, gsum);
+    if (__any_sync(0xffffffffu, (raw[5].x | raw[5].y | raw[5].z | raw[5].w) != 0)) dequant_group<COMP, 5>(p, raw[5], d, gsum);
+    if (__any_sync(0xffffffffu, (raw[6].x | raw[6].y | raw[6].z | raw[6].w) != 0)) dequant_group<COMP, 6>(p, raw[6], d, gsum);
+    if (__any_sync(0xffffffffu, (raw[7].x | raw[7].y | raw[7].z | raw[7].w) != 0)) dequant_group<COMP, 7>(p, raw[7], d, gsum);
+}
+
+// FP64 re-evaluation of one sample of block `cz` (zig-zag int16 coefficients) with quantiser table qt (natural order)
+__device__ __noinline__ int idct_fix(const int16_t* __restrict__ cz, const uint16_t* __restrict__ qt, int x, int y, unsigned long long* counter)
+{
+    double acc = 0.0;
+    for (int n = 0; n < 64; ++n) {
+        const int c = cz[n];
+        if (!c) continue;
+        const int nat = cC.zz[n], v = nat >> 3, u = nat & 7;
+        const double f = double(c * int(qt[nat])) * (u ? 1.0 : 0.70710678118654752440) * (v ? 1.0 : 0.70710678118654752440);
+        acc = fma(f * cC.cos_ref[u * 8 + x], cC.cos_ref[v * 8 + y], acc);
+    }
+    const double val = acc * 0.25 + 128.0;
+    if (fabs(val - rint(val)) >= 1e-9) return __double2int_rz(val);
+    // the reference's exact operation order: natural order ascending, zero terms cannot change the sum
+    double sum = 0.0;
+    for (int nat = 0; nat < 64; ++nat) {
+        const int c = cz[cC.izz[nat]];
+        if (!c) continue;
+        const int v = nat >> 3, u = nat & 7;
+        const double cu = u ? 1.0 : cC.inv_sqrt2_ref, cv = v ? 1.0 : cC.inv_sqrt2_ref;
+        double t = __dmul_rn(cu, cv);
+        t = __dmul_rn(t, double(c * int(qt[nat])));
+        t = __dmul_rn(t, cC.cos_ref[u * 8 + x]);
+        t = __dmul_rn(t, cC.cos_ref[v * 8 + y]);
+        sum = __dadd_rn(sum, t);
+    }
+    atomicAdd(counter, 1ull);
+    return __double2int_rz(__dadd_rn(__dmul_rn(sum, 0.25), 128.0));
+}
+
+constexpr uint32_t kWholeBlock = 1u << 15;   // above the 8-bit block number (blk << 7 occupies bits 7..14)
+
+__device__ __noinline__ void push_fix16(uint32_t* s_nfix, uint16_t* s_fix, uint32_t entry)
+{
+    const uint32_t idx = atomicAdd(s_nfix, 1u);
+    if (idx < kFixCap) s_fix[idx] = uint16_t(entry);
+}
+
+// colour conversion of 4 horizontally adjacent pixels sharing 2 chroma pairs; y4: 4 int16 in two words
+__device__ __noinline__ uint32_t colour_exact4(const int* y, int cb0, int cr0, int cb1, int cr1, int which)
+{
+    uint32_t out = 0;
+    for (int i = 0; i < 4; ++i) {
+        const int cb = i < 2 ? cb0 : cb1, cr = i < 2 ? cr0 : cr1;
+        const uint32_t v = which == 0 ? ref_R(y[i], cr) : (which == 1 ? ref_G(y[i], cb, cr) : ref_B(y[i], cb));
+        out |= v << (8 * i);
+    }
+    return out;
+}
+
+__device__ __forceinline__ uint32_t sat_u8(float v)
+{
+    uint32_t r;
+    asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+
+__global__ void __launch_bounds__(256, 2) k_inv_transform(const __grid_constant__ InvParams p)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* s_coef = smem;                                  // [192][144] zig-zag int16 coefficients (padded)
+    uint8_t* s_y = s_coef + kTileBlk * kOutStride;           // [16][kIYStride] int16 luma samples
+    uint8_t* s_cb = s_y + 16 * kIYStride;                    // [8][kICStride]
+    uint8_t* s_cr = s_cb + 8 * kICStride;
+    uint16_t* s_fix = reinterpret_cast<uint16_t*>(s_cr + 8 * kICStride);
+    uint32_t* s_nfix = reinterpret_cast<uint32_t*>(s_fix + kFixCap);
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t mx0 = blockIdx.x * kTileMcu;
+    const uint32_t my = blockIdx.y;
+    const size_t img = blockIdx.z;
+    const uint32_t nvalid = min(uint32_t(kTileMcu), p.HU - mx0);
+    if (t == 0) *s_nfix = 0;
+
+    // ---- phase 0: coalesced load of the tile's coefficients into the padded staging buffer ----
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.coefs + img * p.coef_stride + (size_t(my) * p.HU + mx0) * 384);
+        const uint32_t nchunks = nvalid * 48;
+        for (uint32_t c = t; c < kTileBlk * 8; c += 256)
+            *reinterpret_cast<uint4*>(&s_coef[(c >> 3) * kOutStride + (c & 7) * 16]) = c < nchunks ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+
+    // ---- phase 1: dequantisation + IDCT, one thread per block (warps 0..3 luma, 4 Cb, 5 Cr) ----
+    if (warp < 6) {
+        uint32_t blk;
+        uint8_t* tile;
+        int stride;
+        if (warp < 4) {
+            const uint32_t mcu = (warp >> 1) * 16 + (lane >> 1), k = (warp & 1) * 2 + (lane & 1);
+            blk = mcu * 6 + k;
+            tile = &s_y[(warp & 1) * 8 * kIYStride + (mcu * 16 + (lane & 1) * 8) * 2];
+            stride = kIYStride;
+        } else {
+            blk = lane * 6 + warp;
+            tile = (warp == 4 ? s_cb : s_cr) + lane * 16;
+            stride = kICStride;
+        }
+        float d[64];
+        float gsum;
+        bool dc_only;
+        const uint4* src = reinterpret_cast<const uint4*>(&s_coef[blk * kOutStride]);
+        if (warp < 4) dequant_block<0>(p, src, d, gsum, dc_only);
+        else if (warp == 4) dequant_block<1>(p, src, d, gsum, dc_only);
+        else dequant_block<2>(p, src, d, gsum, dc_only);
+        d[0] += 128.0f;   // level shift rides on the DC term (gain 1 through the flowgraph)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) aan_idct8(d[u], d[8 + u], d[16 + u], d[24 + u], d[32 + u], d[40 + u], d[48 + u], d[56 + u]);
+#pragma unroll
+        for (int y = 0; y < 8; ++y)
+            aan_idct8(d[y * 8 + 0], d[y * 8 + 1], d[y * 8 + 2], d[y * 8 + 3], d[y * 8 + 4], d[y * 8 + 5], d[y * 8 + 6], d[y * 8 + 7]);
+        // DC-only blocks: the exact value is very often an integer; the whole block is decided in the fix-up pass
+        const float guard = dc_only ? -1.0f : gsum;
+        if (dc_only) push_fix16(s_nfix, s_fix, (blk << 7) | 64u);
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+            int iv[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+                const float val = d[y * 8 + x];
+                iv[x] = __float2int_rz(val);
+                const float kf = (val + 12582912.0f) - 12582912.0f;   // rint(val), |val| < 2^22
+                if (fabsf(val - kf) < guard) push_fix16(s_nfix, s_fix, (blk << 7) | uint32_t(y * 8 + x));
+            }
+            uint4 v;
+            v.x = __byte_perm(uint32_t(iv[0]), uint32_t(iv[1]), 0x5410), v.y = __byte_perm(uint32_t(iv[2]), uint32_t(iv[3]), 0x5410);
+            v.z = __byte_perm(uint32_t(iv[4]), uint32_t(iv[5]), 0x5410), v.w = __byte_perm(uint32_t(iv[6]), uint32_t(iv[7]), 0x5410);
+            *reinterpret_cast<uint4*>(tile + y * stride) = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 1b: dense re-evaluation of the queue (guard-band samples and DC-only blocks) ----
+    {
+        const uint32_t nfix = *s_nfix;
+        if (nfix) {
+            const bool overflow = nfix > kFixCap;
+            const uint32_t ntask = overflow ? kTileBlk * 8u : nfix * 8u;
+            for (uint32_t task = t; task < ntask; task += 256) {
+                // entry = blk << 7 | flags: bit 6 = DC-only block, bits 0..5 = sample; kWholeBlock (overflow only) = every sample
+                const uint32_t e = overflow ? (((task >> 3) << 7) | kWholeBlock) : s_fix[task >> 3];
+                const uint32_t blk = (e >> 7) & 255u, sub = task & 7u;
+                const uint32_t mcu = blk / 6u, k = blk - mcu * 6u;
+                const int comp = k < 4u ? 0 : int(k) - 3;
+                const int16_t* cz = reinterpret_cast<const int16_t*>(&s_coef[blk * kOutStride]);
+                int16_t* tile;
+                int stride;
+                if (k < 4u) {
+                    tile = reinterpret_cast<int16_t*>(&s_y[(k >> 1) * 8 * kIYStride + (mcu * 16 + (k & 1) * 8) * 2]);
+                    stride = kIYStride / 2;
+                } else {
+                    tile = reinterpret_cast<int16_t*>((k == 4u ? s_cb : s_cr) + mcu * 16);
+                    stride = kICStride / 2;
+                }
+                if (e & kWholeBlock) {     // overflow path: row `sub` of the block, every sample in FP64
+                    for (int x = 0; x < 8; ++x) tile[sub * stride + x] = int16_t(idct_fix(cz, p.qt[comp], x, int(sub), p.guard_counter));
+                } else if (e & 64u) {      // DC-only block: ((c*c)*F)*1*1, /4, +128 exactly as the reference evaluates it
+                    const double f = double(int(cz[0]) * int(p.qt[comp][0]));
+                    const double term = __dmul_rn(__dmul_rn(cC.inv_sqrt2_ref, cC.inv_sqrt2_ref), f);
+                    const int v = __double2int_rz(__dadd_rn(__dmul_rn(term, 0.25), 128.0));
+                    const uint32_t vv = __byte_perm(uint32_t(v), uint32_t(v), 0x5410);
+                    *reinterpret_cast<uint4*>(tile + sub * stride) = make_uint4(vv, vv, vv, vv);
+                } else if (sub == 0) {
+                    const int s = int(e & 63u);
+                    tile[(s >> 3) * stride + (s & 7)] = int16_t(idct_fix(cz, p.qt[comp], s & 7, s >> 3, p.guard_counter));
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- phase 2: chroma replication + colour conversion + planar stores; warp = row pair, lane = MCU ----
+    {
+        const uint32_t mx = mx0 + lane;
+        const uint32_t x0 = mx * 16u;
+        if (mx >= p.HU) return;
+        uint8_t* R = p.r + img * p.plane_stride;
+        uint8_t* G = p.g + img * p.plane_stride;
+        uint8_t* B = p.b + img * p.plane_stride;
+        // 8 chroma pairs of this MCU row pair
+        const uint4 cbw = *reinterpret_cast<const uint4*>(&s_cb[warp * kICStride + lane * 16]);
+        const uint4 crw = *reinterpret_cast<const uint4*>(&s_cr[warp * kICStride + lane * 16]);
+        const uint32_t cbv[4] = {cbw.x, cbw.y, cbw.z, cbw.w}, crv[4] = {crw.x, crw.y, crw.z, crw.w};
+        float tr[8], tg[8], tb[8];
+        int cbi[8], cri[8];
+        uint32_t suspect = 0;
+        if (!p.gray) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                cbi[c] = (c & 1) ? (int(cbv[c >> 1]) >> 16) : int(short(cbv[c >> 1] & 0xffffu));
+                cri[c] = (c & 1) ? (int(crv[c >> 1]) >> 16) : int(short(crv[c >> 1] & 0xffffu));
+                const float a = float(cbi[c] - 128), b = float(cri[c] - 128);
+                tr[c] = b * 1.4020f;
+                tb[c] = a * 1.7718f;
+                tg[c] = fmaf(b, -0.7139f, a * -0.3441f);
+                // G is an exact integer only when 3441a + 7139b = 0 (mod 10000); FP32 error of tg < 7.5e-5 for |a|,|b| <= 256
+                const float kf = (tg[c] + 12582912.0f) - 12582912.0f;
+                const bool near_int = fabsf(tg[c] - kf) < 7.5e-5f && (cbi[c] != 128 || cri[c] != 128);
+                const bool wild = uint32_t(cbi[c] + 128) > 512u || uint32_t(cri[c] + 128) > 512u;
+                if (near_int || wild) suspect |= 1u << c;
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int ry = warp * 2 + rr;
+            const uint4 ya = *reinterpret_cast<const uint4*>(&s_y[ry * kIYStride + lane * 32]);
+            const uint4 yb = *reinterpret_cast<const uint4*>(&s_y[ry * kIYStride + lane * 32 + 16]);
+            const uint32_t yw[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+            uint32_t ro[4], go[4], bo[4];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {       // 4 pixels = 2 chroma pairs
+                int yi[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t w = yw[q4 * 2 + (i >> 1)];
+                    yi[i] = (i & 1) ? (int(w) >> 16) : int(short(w & 0xffffu));
+                }
+                if (p.gray) {
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v |= sat_u8(float(yi[i])) << (8 * i);
+                    ro[q4] = go[q4] = bo[q4] = v;
+                } else {
+                    const int c0 = q4 * 2, c1 = q4 * 2 + 1;
+                    if ((suspect >> c0) & 3u) {
+                        ro[q4] = colour_exact4(yi, cbi[c0], cri[c0], cbi[c1], cri[c1], 0);
+                        go[q4] = colour_exact4(yi, cbi[c0], cri[c0], cbi[c1], cri[c1], 1);
+                        bo[q4] = colour_exact4(yi, cbi[c0], cri[c0], cbi[c1], cri[c1], 2);
+                    } else {
+                        uint32_t rv = 0, gv = 0, bv = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float yf = float(yi[i]);
+                            const int c = i < 2 ? c0 : c1;
+                            rv |= sat_u8(yf + tr[c]) << (8 * i);
+                            gv |= sat_u8(yf + tg[c]) << (8 * i);
+                            bv |= sat_u8(yf + tb[c]) << (8 * i);
+                        }
+                        ro[q4] = rv, go[q4] = gv, bo[q4] = bv;
+                    }
+                }
+            }
+            const size_t rowoff = (size_t(my) * 16 + ry) * p.W;
+            if ((p.W & 15u) == 0 && x0 + 16u <= p.W) {
+                *reinterpret_cast<uint4*>(R + rowoff + x0) = make_uint4(ro[0], ro[1], ro[2], ro[3]);
+                *reinterpret_cast<uint4*>(G + rowoff + x0) = make_uint4(go[0], go[1], go[2], go[3]);
+                *reinterpret_cast<uint4*>(B + rowoff + x0) = make_uint4(bo[0], bo[1], bo[2], bo[3]);
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < 16; ++i) {
+                    if (x0 + i >= p.W) break;
+                    R[rowoff + x0 + i] = uint8_t(ro[i >> 2] >> (8 * (i & 3)));
+                    G[rowoff + x0 + i] = uint8_t(go[i >> 2] >> (8 * (i & 3)));
+                    B[rowoff + x0 + i] = uint8_t(bo[i >> 2] >> (8 * (i & 3)));
+                }
+            }
         }
     }
 }
