@@ -237,7 +237,7 @@ __device__ __forceinline__ void dequant_block(const InvParams& p, const uint4* _
 }
 
 // FP64 re-evaluation of one sample of block `cz` (zig-zag int16 coefficients) with quantiser table qt (natural order)
-__device__ __noinline__ int idct_fix(const int16_t* __restrict__ cz, const uint16_t* __restrict__ qt, int x, int y, unsigned long long* counter)
+__device__ __noinline__ int idct_fix(const int16_t* __restrict__ cz, const uint16_t* __restrict__ qt, int x, int y, uint32_t* exact_hits)
 {
     double acc = 0.0;
     for (int n = 0; n < 64; ++n) {
@@ -262,7 +262,7 @@ __device__ __noinline__ int idct_fix(const int16_t* __restrict__ cz, const uint1
         t = __dmul_rn(t, cC.cos_ref[v * 8 + y]);
         sum = __dadd_rn(sum, t);
     }
-    atomicAdd(counter, 1ull);
+    ++*exact_hits;
     return __double2int_rz(__dadd_rn(__dmul_rn(sum, 0.25), 128.0));
 }
 
@@ -373,6 +373,7 @@ __global__ void __launch_bounds__(256, 2) k_inv_transform(const __grid_constant_
         const uint32_t nfix = *s_nfix;
         if (nfix) {
             const bool overflow = nfix > kFixCap;
+            uint32_t exact_hits = 0;    // samples decided by the reference's exact operation order (JPEZYB200_STAT_GUARD_INV)
             const uint32_t ntask = overflow ? kTileBlk * 8u : nfix * 8u;
             for (uint32_t task = t; task < ntask; task += 256) {
                 // entry = blk << 7 | flags: bit 6 = DC-only block, bits 0..5 = sample; kWholeBlock (overflow only) = every sample
@@ -391,18 +392,21 @@ __global__ void __launch_bounds__(256, 2) k_inv_transform(const __grid_constant_
                     stride = kICStride / 2;
                 }
                 if (e & kWholeBlock) {     // overflow path: row `sub` of the block, every sample in FP64
-                    for (int x = 0; x < 8; ++x) tile[sub * stride + x] = int16_t(idct_fix(cz, p.qt[comp], x, int(sub), p.guard_counter));
+                    for (int x = 0; x < 8; ++x) tile[sub * stride + x] = int16_t(idct_fix(cz, p.qt[comp], x, int(sub), &exact_hits));
                 } else if (e & 64u) {      // DC-only block: ((c*c)*F)*1*1, /4, +128 exactly as the reference evaluates it
                     const double f = double(int(cz[0]) * int(p.qt[comp][0]));
                     const double term = __dmul_rn(__dmul_rn(cC.inv_sqrt2_ref, cC.inv_sqrt2_ref), f);
                     const int v = __double2int_rz(__dadd_rn(__dmul_rn(term, 0.25), 128.0));
                     const uint32_t vv = __byte_perm(uint32_t(v), uint32_t(v), 0x5410);
                     *reinterpret_cast<uint4*>(tile + sub * stride) = make_uint4(vv, vv, vv, vv);
+                    exact_hits += 8;
                 } else if (sub == 0) {
                     const int s = int(e & 63u);
-                    tile[(s >> 3) * stride + (s & 7)] = int16_t(idct_fix(cz, p.qt[comp], s & 7, s >> 3, p.guard_counter));
+                    tile[(s >> 3) * stride + (s & 7)] = int16_t(idct_fix(cz, p.qt[comp], s & 7, s >> 3, &exact_hits));
                 }
             }
+            exact_hits = __reduce_add_sync(0xffffffffu, exact_hits);
+            if (lane == 0 && exact_hits) atomicAdd(p.guard_counter, (unsigned long long)exact_hits);
             __syncthreads();
         }
     }
