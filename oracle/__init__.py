@@ -23,6 +23,62 @@ def build(force=False):
     return so
 
 
+def ref_dir():
+    """oracle/_ref: the reference's own sources compiled against oracle/shim (None when it was never built)."""
+    d = os.path.join(_HERE, "_ref")
+    return d if os.path.exists(os.path.join(d, "libjpezy_ref.so")) else None
+
+
+class Reference:
+    """The reference's own encoder / decoder classes (oracle/ref_driver.cpp).  File based, like the reference."""
+
+    def __init__(self):
+        d = ref_dir()
+        if d is None:
+            raise RuntimeError("oracle/_ref is not built (needs /root/reference: `make -C oracle ref`)")
+        L = self.lib = C.CDLL(os.path.join(d, "libjpezy_ref.so"))
+        L.ref_encode_file.restype = C.c_longlong
+        L.ref_encode_file.argtypes = [_u8p, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_char_p]
+        L.ref_constants.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        self.encode_exe = os.path.join(d, "jpezy_encode")
+        self.decode_exe = os.path.join(d, "jpezy_decode")
+        self.tool = os.path.join(d, "ref_tool")
+
+    def encode(self, r, g, b, W, H, gray=False, path=None):
+        """-> (file bytes, wrote_size()) of jpezy::encoder(...).encode<MODE>(path)"""
+        import tempfile
+        r, g, b = (np.ascontiguousarray(x, dtype=np.uint8).reshape(-1) for x in (r, g, b))
+        with tempfile.TemporaryDirectory() as tmp:
+            p = path or os.path.join(tmp, "ref.jpg")
+            n = self.lib.ref_encode_file(_ptr(r), _ptr(g), _ptr(b), W, H, int(gray), p.encode())
+            if n < 0:
+                raise RuntimeError("reference encoder threw")
+            return open(p, "rb").read(), int(n)
+
+    def decode(self, data, gray=False):
+        """-> (W, H, r, g, b) of jpezy::decoder<Release>(file).decode<MODE>(); None when decode() returns an empty optional.
+        Runs in a process of its own (oracle/_ref/ref_tool): the reference's analyze_dht reads one element past a vector
+        (src/decoder/jpezy_decoder.hpp:231), harmless in a fresh process, heap-corrupting inside a long-lived one."""
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            p, out = os.path.join(tmp, "ref.jpg"), os.path.join(tmp, "ref.bin")
+            open(p, "wb").write(data)
+            rc = subprocess.run([self.tool, "decode", p, str(int(gray)), out], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode
+            if rc:
+                return None
+            raw = np.fromfile(out, dtype=np.uint8)
+            W, H = (int(x) for x in raw[:8].view(np.int32))
+            pl = int(raw[8:16].view(np.uint64)[0])
+            r, g, b = (raw[16 + k * pl: 16 + (k + 1) * pl].copy() for k in range(3))
+            return W, H, r, g, b
+
+    def constants(self):
+        cos = np.zeros(64, np.float64)
+        ds = C.c_double(0)
+        self.lib.ref_constants(_ptr(cos, C.POINTER(C.c_double)), C.byref(ds))
+        return cos, ds.value
+
+
 def _ptr(a, t=_u8p):
     return a.ctypes.data_as(t)
 
