@@ -88,17 +88,27 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def cpu_arm():
+    """The reference's CPU implementation of the path: oracle/_ref (the reference's own sources compiled against
+    oracle/shim, SURVEY.md 8c / DESIGN.md) when it was built, else the oracle port.  -> (timer, kind)
+    timer(r, g, b, W, H, gray, reps, ninstances) -> (wall s, encode s, decode s)"""
+    import oracle as orc
+    if orc.ref_dir() is not None:
+        ref = orc.Reference()
+        return ref.time_roundtrip, "reference"
+    orc.build()
+    o = orc.Oracle("shipped")      # the reference's Release flags (compiler_settings.cmake:4)
+    return o.time_roundtrip, "port"
+
+
 def run_reference(args, wl):
-    """--impl reference: the reference's CPU implementation of the path (the oracle port: the reference itself
-    needs SrookCppLibraries/Boost) on all host cores, bounded sample per step."""
+    """--impl reference: the reference's own encoder::encode() + decoder::decode() on all host cores (one instance per
+    core, the reference is single threaded), each step a bounded sample of the workload image."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
     import jpezy_b200 as J
-    import oracle as orc
-    orc.build()
-    o = orc.Oracle("shipped")      # the reference's Release flags (compiler_settings.cmake:4)
+    timer, kind = cpu_arm()
     cores = os.cpu_count() or 1
     W, H = wl["W"], wl["H"]
     # bounded sample: a band of MCU rows of the workload image, sized for ~120 s total at ~2.7 MPix/s/core round trip
@@ -106,25 +116,25 @@ def run_reference(args, wl):
     rows = int(min(H, max(16, (budget_px // W) // 16 * 16)))
     r, g, b = J.synth.image(0, W, rows, frame=0)
     for _ in range(args.warmup):
-        o.time_roundtrip(r, g, b, W, rows, wl["gray"], 1, cores)
-    t0 = time.perf_counter()
-    te = td = 0.0
+        timer(r, g, b, W, rows, wl["gray"], 1, cores)
+    dt = te = td = 0.0
     for _ in range(args.steps):
-        _, e, d = o.time_roundtrip(r, g, b, W, rows, wl["gray"], 1, cores)
+        w, e, d = timer(r, g, b, W, rows, wl["gray"], 1, cores)
+        dt += w
         te += e
         td += d
-    dt = time.perf_counter() - t0
     px = float(W) * rows * cores * args.steps
     val = px / dt / 1e6
-    sample = "%dx%d band (%d of %d rows) of the workload image, one instance per core, encode()+decode() in memory" % (W, rows, rows, H)
+    sample = "%dx%d band (%d of %d rows) of the workload image per instance, %d concurrent single-threaded instances, " \
+             "encode()+decode() per step, PNM I/O excluded" % (W, rows, rows, H, cores)
     line = {"impl": "reference", "metric": "encode+decode MPix/s", "value": val, "unit": "MPix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "width": W, "height": H, "batch_per_gpu": wl["batch"], "gray": wl["gray"],
                        "family": "S-photo"},
-            "cpu_baseline": {"value": val, "unit": "MPix/s", "cores": cores, "kind": "port", "sample": sample,
-                             "encode_MPix_s": px / (te / 1.0) / 1e6 * 1.0 if te else None,
-                             "decode_MPix_s": px / (td / 1.0) / 1e6 * 1.0 if td else None},
+            "cpu_baseline": {"value": val, "unit": "MPix/s", "cores": cores, "kind": kind, "sample": sample,
+                             "encode_MPix_s_per_core": float(W) * rows * args.steps / te / 1e6 if te else None,
+                             "decode_MPix_s_per_core": float(W) * rows * args.steps / td / 1e6 if td else None},
             "e2e": {"value": val, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -327,19 +337,17 @@ def main():
     # ---- CPU baseline: the oracle port on the host cores, rank 0 at N=1 only, bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import oracle as orc
-        orc.build()
-        o = orc.Oracle("shipped")
+        timer, kind = cpu_arm()
         rows = min(H, 1024)
         r, g, b = (d_in[0, c, 0, :rows].cpu().numpy() for c in range(3))
-        wall1, te1, td1 = o.time_roundtrip(r, g, b, W, rows, gray, 1, 1)
+        wall1, te1, td1 = timer(r, g, b, W, rows, gray, 1, 1)
         cores = os.cpu_count() or 1
-        wallc, _, _ = o.time_roundtrip(r, g, b, W, rows, gray, 1, cores)
+        wallc, _, _ = timer(r, g, b, W, rows, gray, 1, cores)
         px = float(W) * rows
-        cpu = {"value": px / wall1 / 1e6, "unit": "MPix/s", "cores": 1, "kind": "port",
-               "sample": "%dx%d band (first %d rows) of one workload frame, 1 round trip, encode()+decode() in memory, PPM I/O excluded" % (W, rows, rows),
+        cpu = {"value": px / wall1 / 1e6, "unit": "MPix/s", "cores": 1, "kind": kind,
+               "sample": "%dx%d band (first %d rows) of one workload frame, 1 round trip, encode()+decode(), PNM I/O excluded" % (W, rows, rows),
                "encode_MPix_s": px / te1 / 1e6, "decode_MPix_s": px / td1 / 1e6,
-               "all_cores": {"cores": cores, "value": px * cores / wallc / 1e6, "how": "one instance per core (threads)"}}
+               "all_cores": {"cores": cores, "value": px * cores / wallc / 1e6, "how": "one single-threaded instance per core"}}
 
     if rank == 0:
         line = {"metric": "encode+decode MPix/s", "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,

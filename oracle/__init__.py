@@ -72,6 +72,27 @@ class Reference:
             r, g, b = (raw[16 + k * pl: 16 + (k + 1) * pl].copy() for k in range(3))
             return W, H, r, g, b
 
+    def time_roundtrip(self, r, g, b, W, H, gray=False, reps=1, nprocs=1):
+        """nprocs concurrent instances of `ref_tool bench` (one per core), each `reps` x (encode() + decode()) of the image.
+        -> (wall seconds of the slowest instance's timed region, mean encode seconds, mean decode seconds) per instance"""
+        import tempfile
+        r, g, b = (np.ascontiguousarray(x, dtype=np.uint8).reshape(-1) for x in (r, g, b))
+        tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            src = os.path.join(tmp, "in.rgb")
+            np.concatenate([r, g, b]).tofile(src)
+            ps = [subprocess.Popen([self.tool, "bench", src, str(W), str(H), str(int(gray)), str(reps), os.path.join(tmp, "s%d.jpg" % i)],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL) for i in range(nprocs)]
+            outs = [p.communicate()[0].split() for p in ps]
+            if any(p.returncode for p in ps):
+                raise RuntimeError("ref_tool bench failed")
+            te = [float(o[0]) for o in outs]
+            td = [float(o[1]) for o in outs]
+            return max(a + c for a, c in zip(te, td)), sum(te) / nprocs, sum(td) / nprocs
+        finally:
+            import shutil
+            shutil.rmtree(tmp, ignore_errors=True)
+
     def constants(self):
         cos = np.zeros(64, np.float64)
         ds = C.c_double(0)

@@ -2,6 +2,7 @@
 // compiled unmodified from /root/reference/src against oracle/shim (see oracle/shim/README.md for what that pins and
 // what it does not).  Output: oracle/_ref/libjpezy_ref.so (git-ignored).  Used by tests/golden/make_golden.py and
 // tests/test_oracle_vs_ref.py to validate the restatement in jpezy_oracle.cpp; never by the product.
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -105,7 +106,32 @@ int main(int argc, char** argv)
         std::fclose(fp);
         return 0;
     }
-    std::fprintf(stderr, "usage: ref_tool decode <in.jpg> <gray 0|1> <out.bin>\n");
+    // ref_tool bench <in.rgb> <W> <H> <gray 0|1> <reps> <scratch.jpg>: times encoder::encode() (header + MCU loop + EOI + the
+    // single fwrite of the buffer, src/encoder/jpezy_encoder.hpp:38-77) and decoder::decode() (marker parse + MCU loop,
+    // src/decoder/jpezy_decoder.hpp:76-134) the way the CLIs call them; PNM parsing / writing is not part of either.
+    // in.rgb = the three planes back to back.  Prints "<encode seconds> <decode seconds>" (sums over reps).
+    if (argc == 8 && std::string(argv[1]) == "bench") {
+        const int W = std::atoi(argv[3]), H = std::atoi(argv[4]), gray = std::atoi(argv[5]), reps = std::atoi(argv[6]);
+        const std::size_t n = std::size_t(W) * std::size_t(H);
+        std::vector<std::uint8_t> in(3 * n);
+        std::FILE* fp = std::fopen(argv[2], "rb");
+        if (!fp || std::fread(in.data(), 1, in.size(), fp) != in.size()) return 2;
+        std::fclose(fp);
+        double te = 0, td = 0;
+        for (int i = 0; i < reps; ++i) {
+            const auto t0 = std::chrono::steady_clock::now();
+            if (ref_encode_file(in.data(), in.data() + n, in.data() + 2 * n, W, H, gray, argv[7]) < 0) return 3;
+            const auto t1 = std::chrono::steady_clock::now();
+            int w2 = 0, h2 = 0;
+            std::size_t pl = 0;
+            if (ref_decode_file(argv[7], gray, &w2, &h2, &pl, nullptr, nullptr, nullptr, 0)) return 4;
+            const auto t2 = std::chrono::steady_clock::now();
+            te += std::chrono::duration<double>(t1 - t0).count(), td += std::chrono::duration<double>(t2 - t1).count();
+        }
+        std::printf("%.6f %.6f\n", te, td);
+        return 0;
+    }
+    std::fprintf(stderr, "usage: ref_tool decode <in.jpg> <gray 0|1> <out.bin> | bench <in.rgb> <W> <H> <gray> <reps> <scratch.jpg>\n");
     return 2;
 }
 #endif
