@@ -167,10 +167,51 @@ JPEZYB200_API int jpezyb200_entropy_decode_dev(jpezyb200_ctx* ctx, const uint8_t
 JPEZYB200_API int jpezyb200_transform_inv_dev(jpezyb200_ctx* ctx, const int16_t* d_coefs, const jpezyb200_frame* f, uint32_t nimg,
                                 int gray, uint8_t* d_r, uint8_t* d_g, uint8_t* d_b, size_t plane_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * One image, several GPUs: the encoder sharded by MCU rows (BASELINE.json config 5).  No counterpart in the
+ * reference (single threaded); the OUTPUT is the reference's: one restart-less segment, byte-identical to
+ * jpezyb200_encode on the whole image.  One context (one process) per GPU; the four phases are separated by
+ * three tiny all-gathers that the caller performs (NCCL through torch.distributed in jpezy_b200/shard.py):
+ *
+ *   a: transform the shard's MCU rows                 -> d_last_dc[3]   (quantised DC of Y3, Cb, Cr of the last MCU)
+ *      all-gather #1; rank k passes rank k-1's record (rank 0: zeros) as d_dc_init: the running predictors
+ *      pre_DC[3] of src/encoder/jpezy_encoder.hpp:180-181 crossing the shard boundary
+ *   b: code lengths, local scan, bit scatter          -> d_info[2]      {local bit count, first 8 local bits}
+ *      all-gather #2 -> d_all_info[nranks][2]
+ *   c: global bit base, ownership of aligned bytes, 0xFF count of the owned bytes (byte stuffing depends on the global
+ *      byte alignment)                                -> d_out_bytes[1] owned + stuffed bytes of this rank
+ *      all-gather #3 -> d_all_bytes[nranks]
+ *   d: stuffed bytes written at this rank's byte base straight into d_dst, the stitched stream, which may live on
+ *      another GPU (jpezyb200_ipc_*): the stores go over NVLink, there is no staging copy.
+ *
+ * Planes passed to phase a hold image rows y_origin.. (row stride W); the shard covers MCU rows
+ * [mcu_row0, mcu_row0 + mcu_rows) and needs pixel rows mcu_row0*16 .. min(H, (mcu_row0+mcu_rows)*16) - 1.
+ * d_total_bytes (may be NULL) receives the length of the whole stream, d_overflow (may be NULL) 1 when it did
+ * not fit dst_cap or a rank's scratch.
+ * ---------------------------------------------------------------------------------------------- */
+JPEZYB200_API int jpezyb200_shard_encode_a(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g, const uint8_t* d_b, uint32_t W,
+                             uint32_t H, uint32_t mcu_row0, uint32_t mcu_rows, uint32_t y_origin, int gray, int32_t* d_last_dc,
+                             void* stream);
+JPEZYB200_API int jpezyb200_shard_encode_b(jpezyb200_ctx* ctx, const int32_t* d_dc_init, uint64_t* d_info, void* stream);
+JPEZYB200_API int jpezyb200_shard_encode_c(jpezyb200_ctx* ctx, const uint64_t* d_all_info, uint32_t rank, uint32_t nranks,
+                             uint64_t* d_out_bytes, void* stream);
+JPEZYB200_API int jpezyb200_shard_encode_d(jpezyb200_ctx* ctx, const uint64_t* d_all_bytes, uint8_t* d_dst, size_t dst_cap,
+                             uint64_t* d_total_bytes, int32_t* d_overflow, void* stream);
+
+/* Peer-visible device buffer for the stitched stream: the owning rank allocates and exports a 64-byte CUDA IPC
+ * handle, the other ranks (other processes, other GPUs of the box) map it and pass the mapped pointer as d_dst. */
+JPEZYB200_API int jpezyb200_ipc_alloc(jpezyb200_ctx* ctx, size_t bytes, void** d_ptr, uint8_t handle[64]);
+JPEZYB200_API int jpezyb200_ipc_open(jpezyb200_ctx* ctx, const uint8_t handle[64], void** d_ptr);
+JPEZYB200_API int jpezyb200_ipc_close(jpezyb200_ctx* ctx, void* d_ptr);
+JPEZYB200_API int jpezyb200_ipc_free(jpezyb200_ctx* ctx, void* d_ptr);
+
 /* Synthetic planar RGB generator, pure integer arithmetic, identical to
  * jpezy_b200.synth on the host.  family: 0 = S-photo, 1 = S-noise, 2 = flat/ramps (adversarial). */
 JPEZYB200_API int jpezyb200_synth_dev(jpezyb200_ctx* ctx, uint8_t* d_r, uint8_t* d_g, uint8_t* d_b, uint32_t W, uint32_t H,
                         uint32_t nimg, uint32_t first_frame, int family, void* stream);
+/* rows y0 .. y0+nrows-1 of frame `frame` of a W-wide image (the shards of one giant image generate their own rows) */
+JPEZYB200_API int jpezyb200_synth_rows_dev(jpezyb200_ctx* ctx, uint8_t* d_r, uint8_t* d_g, uint8_t* d_b, uint32_t W, uint32_t y0,
+                             uint32_t nrows, uint32_t frame, int family, void* stream);
 
 #ifdef __cplusplus
 }

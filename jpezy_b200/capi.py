@@ -15,7 +15,9 @@ EXPORTS = [
     "jpezyb200_set_option", "jpezyb200_get_stat", "jpezyb200_encode", "jpezyb200_encode_batch_dev",
     "jpezyb200_transform_fwd_dev", "jpezyb200_entropy_encode_dev", "jpezyb200_plane_bytes", "jpezyb200_default_frame",
     "jpezyb200_decode", "jpezyb200_decode_batch_dev", "jpezyb200_entropy_decode_dev", "jpezyb200_transform_inv_dev",
-    "jpezyb200_synth_dev",
+    "jpezyb200_synth_dev", "jpezyb200_synth_rows_dev", "jpezyb200_shard_encode_a", "jpezyb200_shard_encode_b",
+    "jpezyb200_shard_encode_c", "jpezyb200_shard_encode_d", "jpezyb200_ipc_alloc", "jpezyb200_ipc_open", "jpezyb200_ipc_close",
+    "jpezyb200_ipc_free",
 ]
 
 
@@ -81,6 +83,15 @@ def load_library():
     L.jpezyb200_entropy_decode_dev.argtypes = [vp, u8p, sz, u64p, u32, C.POINTER(Frame), i16p, vp, vp]
     L.jpezyb200_transform_inv_dev.argtypes = [vp, i16p, C.POINTER(Frame), u32, C.c_int, u8p, u8p, u8p, sz, vp]
     L.jpezyb200_synth_dev.argtypes = [vp, u8p, u8p, u8p, u32, u32, u32, u32, C.c_int, vp]
+    L.jpezyb200_synth_rows_dev.argtypes = [vp, u8p, u8p, u8p, u32, u32, u32, u32, C.c_int, vp]
+    L.jpezyb200_shard_encode_a.argtypes = [vp, u8p, u8p, u8p, u32, u32, u32, u32, u32, C.c_int, vp, vp]
+    L.jpezyb200_shard_encode_b.argtypes = [vp, vp, vp, vp]
+    L.jpezyb200_shard_encode_c.argtypes = [vp, vp, u32, u32, vp, vp]
+    L.jpezyb200_shard_encode_d.argtypes = [vp, vp, u8p, sz, vp, vp, vp]
+    L.jpezyb200_ipc_alloc.argtypes = [vp, sz, C.POINTER(vp), C.c_char_p]
+    L.jpezyb200_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.jpezyb200_ipc_close.argtypes = [vp, vp]
+    L.jpezyb200_ipc_free.argtypes = [vp, vp]
     _LIB = L
     return L
 
@@ -204,3 +215,39 @@ class Context:
 
     def synth_dev(self, d_r, d_g, d_b, W, H, nimg=1, first_frame=0, family=0, stream=None):
         self._chk(self.lib.jpezyb200_synth_dev(self.h, _dp(d_r), _dp(d_g), _dp(d_b), W, H, nimg, first_frame, family, stream))
+
+    def synth_rows_dev(self, d_r, d_g, d_b, W, y0, nrows, frame=0, family=0, stream=None):
+        self._chk(self.lib.jpezyb200_synth_rows_dev(self.h, _dp(d_r), _dp(d_g), _dp(d_b), W, y0, nrows, frame, family, stream))
+
+    # ---- MCU-row sharded encoder (one image, several GPUs): see jpezy_b200/shard.py for the orchestration ----
+    def shard_encode_a(self, d_r, d_g, d_b, W, H, mcu_row0, mcu_rows, y_origin, gray, d_last_dc, stream=None):
+        self._chk(self.lib.jpezyb200_shard_encode_a(self.h, _dp(d_r), _dp(d_g), _dp(d_b), W, H, mcu_row0, mcu_rows, y_origin, int(gray),
+                                                    _dp(d_last_dc), stream))
+
+    def shard_encode_b(self, d_dc_init, d_info, stream=None):
+        self._chk(self.lib.jpezyb200_shard_encode_b(self.h, _dp(d_dc_init), _dp(d_info), stream))
+
+    def shard_encode_c(self, d_all_info, rank, nranks, d_out_bytes, stream=None):
+        self._chk(self.lib.jpezyb200_shard_encode_c(self.h, _dp(d_all_info), rank, nranks, _dp(d_out_bytes), stream))
+
+    def shard_encode_d(self, d_all_bytes, d_dst, dst_cap, d_total_bytes=None, d_overflow=None, stream=None):
+        self._chk(self.lib.jpezyb200_shard_encode_d(self.h, _dp(d_all_bytes), _dp(d_dst), dst_cap, _dp(d_total_bytes), _dp(d_overflow),
+                                                    stream))
+
+    def ipc_alloc(self, nbytes):
+        """-> (device pointer, 64-byte handle) of a peer-visible buffer owned by this context"""
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        self._chk(self.lib.jpezyb200_ipc_alloc(self.h, nbytes, C.byref(p), h))
+        return p.value, h.raw
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        self._chk(self.lib.jpezyb200_ipc_open(self.h, handle, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._chk(self.lib.jpezyb200_ipc_close(self.h, ptr))
+
+    def ipc_free(self, ptr):
+        self._chk(self.lib.jpezyb200_ipc_free(self.h, ptr))

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -13,6 +14,7 @@
 #include "dec_transform.cuh"
 #include "enc_entropy.cuh"
 #include "enc_transform.cuh"
+#include "enc_shard.cuh"
 #include "synth.cuh"
 
 namespace jz {
@@ -148,13 +150,14 @@ void jpezyb200_ctx_destroy(jpezyb200_ctx* ctx)
     jz_devbuf* bufs[] = {&ctx->coefs, &ctx->blk_off, &ctx->tile_sum, &ctx->tile_base, &ctx->img_bits, &ctx->ustream,
                          &ctx->ff_sum, &ctx->ff_base, &ctx->planes_in, &ctx->planes_out, &ctx->scan_io, &ctx->sizes_io,
                          &ctx->dec_scanbytes, &ctx->dec_chunk_cnt, &ctx->dec_chunk_base, &ctx->dec_ubytes, &ctx->dec_state,
-                         &ctx->dec_dirty, &ctx->dec_subblk, &ctx->dec_dc, &ctx->dec_status, &ctx->dec_changed};
+                         &ctx->dec_dirty, &ctx->dec_subblk, &ctx->dec_dc, &ctx->dec_status, &ctx->dec_changed, &ctx->shard_geom};
     for (jz_devbuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_enc_lut) cudaFree(ctx->d_enc_lut);
     if (ctx->d_dec_lut) cudaFree(ctx->d_dec_lut);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_y_exact) cudaFree(ctx->d_y_exact);
+    std::free(ctx->shard_state);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -359,7 +362,22 @@ int jpezyb200_synth_dev(jpezyb200_ctx* ctx, uint8_t* d_r, uint8_t* d_g, uint8_t*
     JZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t npx = size_t(W) * H;
     const uint32_t gx = uint32_t(std::min<size_t>((npx + 255) / 256, 148 * 16));
-    k_synth<<<dim3(gx, nimg), 256, 0, pick_stream(ctx, stream)>>>(d_r, d_g, d_b, W, H, first_frame, family);
+    k_synth<<<dim3(gx, nimg), 256, 0, pick_stream(ctx, stream)>>>(d_r, d_g, d_b, W, H, first_frame, family, 0u);
+    ++ctx->launches;
+    JZ_CUDA_TRY(ctx, cudaGetLastError());
+    return JPEZYB200_OK;
+}
+
+int jpezyb200_synth_rows_dev(jpezyb200_ctx* ctx, uint8_t* d_r, uint8_t* d_g, uint8_t* d_b, uint32_t W, uint32_t y0, uint32_t nrows,
+                             uint32_t frame, int family, void* stream)
+{
+    int rc = check_geometry(ctx, W, nrows, 1);
+    if (rc) return rc;
+    if (!d_r || !d_g || !d_b) return ctx->fail(JPEZYB200_EINVAL, "null pointer");
+    JZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t npx = size_t(W) * nrows;
+    const uint32_t gx = uint32_t(std::min<size_t>((npx + 255) / 256, 148 * 16));
+    k_synth<<<dim3(gx, 1), 256, 0, pick_stream(ctx, stream)>>>(d_r, d_g, d_b, W, nrows, frame, family, y0);
     ++ctx->launches;
     JZ_CUDA_TRY(ctx, cudaGetLastError());
     return JPEZYB200_OK;
@@ -368,3 +386,4 @@ int jpezyb200_synth_dev(jpezyb200_ctx* ctx, uint8_t* d_r, uint8_t* d_g, uint8_t*
 }  // extern "C"
 
 #include "capi_decode.inc"
+#include "capi_shard.inc"

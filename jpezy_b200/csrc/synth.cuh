@@ -36,13 +36,13 @@ __host__ __device__ inline uint8_t synth_pixel(int family, uint32_t W, uint32_t 
 }
 
 __global__ void __launch_bounds__(256) k_synth(uint8_t* r, uint8_t* g, uint8_t* b, uint32_t W, uint32_t H, uint32_t first_frame,
-                                               int family)
+                                               int family, uint32_t y0)
 {
     const size_t npx = size_t(W) * H;
     const size_t img = blockIdx.y;
     const uint32_t frame = first_frame + uint32_t(img);
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < npx; i += size_t(gridDim.x) * blockDim.x) {
-        const uint32_t y = uint32_t(i / W), x = uint32_t(i - size_t(y) * W);
+        const uint32_t yl = uint32_t(i / W), x = uint32_t(i - size_t(yl) * W), y = y0 + yl;   // H rows starting at image row y0
         r[img * npx + i] = synth_pixel(family, W, x, y, frame, 0);
         g[img * npx + i] = synth_pixel(family, W, x, y, frame, 1);
         b[img * npx + i] = synth_pixel(family, W, x, y, frame, 2);

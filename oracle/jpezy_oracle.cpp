@@ -147,6 +147,7 @@ struct BitWriter {
     size_t cap;
     uint32_t acc = 0;
     int nacc = 0;     // bits pending in acc (0..7)
+    uint64_t total_bits = 0;   // bits written through bits(), fill bits of align() included
     bool pad_ones;
     explicit BitWriter(size_t capacity, bool pad1) : cap(capacity), pad_ones(pad1) { buf.reserve(capacity < (1u << 20) ? capacity : (1u << 20)); }
     void put_raw(uint8_t b)
@@ -156,6 +157,7 @@ struct BitWriter {
     }
     void bits(int n, int v)
     {
+        total_bits += uint64_t(n > 0 ? n : 0);
         for (int i = n - 1; i >= 0; --i) {
             acc = (acc << 1) | ((static_cast<unsigned>(v) >> i) & 1u);
             if (++nacc == 8) {
@@ -738,7 +740,7 @@ int orc_scan_from_coefs(const int16_t* coefs, size_t nmcu, int pad_ones, uint8_t
     try {
         orc::BitWriter w(cap, pad_ones != 0);
         orc::encode_from_coefs(coefs, nmcu, w);
-        (void)nbits;
+        if (nbits) *nbits = w.total_bits;   // before the fill bits
         w.align();
         *out_len = w.buf.size();
         std::memcpy(out, w.buf.data(), w.buf.size());
