@@ -27,6 +27,7 @@ WORKLOADS = {
     "c3": dict(W=1920, H=1080, batch=64, gray=False, name="C3: batch of 1920x1080 RGB frames sharded by image, encode+decode"),
     "c4": dict(W=8192, H=8192, batch=1, gray=True, name="C4: single 8192x8192 --gray image, encode+decode"),
     "c1": dict(W=512, H=512, batch=1, gray=False, name="C1: single 512x512 RGB image, encode+decode"),
+    "c5": dict(W=32768, H=32768, batch=1, gray=False, name="C5: single 32768x32768 RGB image, encode split by MCU rows across the GPUs"),
 }
 FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -139,6 +140,104 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
+def run_sharded(args, wl):
+    """C5: ONE giant image, encode only, sharded by MCU rows over the ranks (strong scaling): transform local rows,
+    all-gather DC predictors / bit counts / byte counts (NCCL), stitched stream written into rank 0's buffer over NVLink."""
+    import numpy as np
+    import torch
+    import jpezy_b200 as J
+    from jpezy_b200 import capi, shard
+    args.steps = args.steps or 20
+    args.warmup = max(args.warmup if args.warmup is not None else 3, 3)
+    rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    ctx = J.Context(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sp = stream.cuda_stream
+    W, H, gray = args.width or wl["W"], args.height or wl["H"], wl["gray"]
+    VU = (H + 15) // 16
+    row0, nrows = shard.partition_mcu_rows(VU, world)[rank]
+    y0, ny = shard.pixel_rows(H, row0, nrows)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    planes = torch.empty((3, ny, W), dtype=torch.uint8, device="cuda")       # > L2 on every rank for the named shape
+    ctx.synth_rows_dev(planes[0], planes[1], planes[2], W, y0, ny, frame=0, family=args.family, stream=sp)
+    grp = shard.DistGroup(dist, torch.device("cuda", local_rank))
+    dst_cap = max(W * H // 2, 1 << 20)
+    enc = shard.ShardedEncoder(ctx, grp, dst_cap)
+
+    def step():
+        enc.encode(planes[0], planes[1], planes[2], W, H, row0, nrows, y0, gray, stream=sp)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler.mark = True
+    l0 = ctx.stat(capi.STAT_KERNEL_LAUNCHES)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.stat(capi.STAT_KERNEL_LAUNCHES) - l0
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # the dominant kernel: forward transform of the local rows
+    def fwd():
+        ctx.shard_encode_a(planes[0], planes[1], planes[2], W, H, row0, nrows, y0, gray, enc.last_dc, stream=sp)
+    for _ in range(3):
+        fwd()
+    torch.cuda.synchronize()
+    a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(10):
+        fwd()
+    b2.record(stream)
+    torch.cuda.synchronize()
+    t_fwd = a.elapsed_time(b2) / 10
+    sampler.mark = None
+    seg, bits = enc.result()
+    sampler.stop_flag = True
+    peak, peak_src = measured_peak()
+    alg = 6.0 * W * 16 * nrows
+    if rank == 0:
+        value = float(W) * H * args.steps / (ms * 1e-3) / 1e6
+        line = {"metric": "encode MPix/s", "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": wl["name"], "width": W, "height": H, "gray": gray, "family": "S-photo" if args.family == 0 else "S-noise",
+                           "l2": "inputs larger than L2 (%.0f MB of planes per rank)" % (3.0 * ny * W / 1e6),
+                           "sharding": "MCU rows, %d per rank; 3 all-gathers (12 B, 16 B, 8 B per rank) + P2P stores of the stuffed segment into rank 0" % nrows},
+                "clocks": sampler.summary(), "gpu_launches": int(launches), "e2e": None,
+                "roofline": {"bound": "hbm", "kernel": "k_fwd_transform", "achieved": alg / (t_fwd * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg / (t_fwd * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg, "ms_per_launch": t_fwd},
+                "cpu_baseline": None,
+                "stages": {"stream_bytes": len(seg), "bits_per_rank": bits, "fwd_transform_ms_rank0": t_fwd}}
+        print(json.dumps(line))
+    enc.close()
+    dist.destroy_process_group()
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -149,6 +248,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step (c3)")
     ap.add_argument("--family", type=int, default=0, help="0 S-photo, 1 S-noise")
     ap.add_argument("--ring", type=int, default=None, help="distinct input/output frame sets rotated between steps")
+    ap.add_argument("--width", type=int, default=None, help="c5: override the image width")
+    ap.add_argument("--height", type=int, default=None, help="c5: override the image height")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -159,6 +260,8 @@ def main():
         args.steps = args.steps or 5
         args.warmup = args.warmup if args.warmup is not None else 1
         return run_reference(args, wl)
+    if args.workload == "c5":
+        return run_sharded(args, wl)
     args.steps = args.steps or 200
     args.warmup = args.warmup if args.warmup is not None else 10
     args.warmup = max(args.warmup, 3)
