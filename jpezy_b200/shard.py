@@ -118,7 +118,11 @@ class ShardedEncoder:
             self.dst = self._mapped
 
     def encode(self, d_r, d_g, d_b, W, H, row0, nrows, y_origin, gray=False, stream=None):
-        """all ranks call this together; planes hold image rows y_origin.. of this rank's shard"""
+        """all ranks call this together; planes hold image rows y_origin.. of this rank's shard.  `stream` must be the raw handle
+        of torch's CURRENT stream and not the legacy default stream (0 / None selects the context's private stream, which
+        the collectives of torch.distributed are not ordered with)"""
+        if not stream:
+            raise ValueError("ShardedEncoder.encode needs torch's current non-default stream (torch.cuda.Stream)")
         c, g = self.ctx, self.group
         c.shard_encode_a(d_r, d_g, d_b, W, H, row0, nrows, y_origin, gray, self.last_dc, stream=stream)
         g.all_gather(self.all_dc, self.last_dc)

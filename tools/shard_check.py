@@ -22,7 +22,12 @@ def main():
     row0, nrows = shard.partition_mcu_rows((H + 15) // 16, world)[rank]
     y0, ny = shard.pixel_rows(H, row0, nrows)
     planes = torch.empty((3, ny, W), dtype=torch.uint8, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    # a real (non-default) stream: the C ABI reads a NULL stream as "the context's own stream", which the NCCL collectives
+    # of torch.distributed would not be ordered with
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream
+    assert st != 0
     ctx.synth_rows_dev(planes[0], planes[1], planes[2], W, y0, ny, frame=0, family=fam, stream=st)
     enc = shard.ShardedEncoder(ctx, shard.DistGroup(dist, torch.device("cuda", lr)), max(W * H, 1 << 20))
     ok = True
