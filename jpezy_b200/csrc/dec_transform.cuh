@@ -158,10 +158,28 @@ __global__ void __launch_bounds__(kFwdThreads) k_inv_transform_f64(const InvPara
 
 // =====================================================================================================
 // Production kernel
+//
+//  * tile = 16 rows x 512 pixels (32 MCUs, 192 blocks) per CTA of 192 threads, 3 CTAs/SM
+//  * phase 0: 16-byte coalesced loads of the tile's coefficients into a padded staging buffer; a ballot over the 8
+//    chunks of a block yields the mask of its non-zero zig-zag groups
+//  * phase 1: one thread per block (warps 0..3 luma, 4 Cb, 5 Cr): dequantisation folded with the AAN input scaling, FP32
+//    AAN IDCT in registers.  When no block of the warp has a coefficient beyond zig-zag position 7 the transform is
+//    pruned (4 three-input column passes + 8 four-input row passes, operations on structural zeros dropped, so the
+//    results are bit-identical to the full flowgraph).  A sample is decided when it is further than the block's guard
+//    band from an integer (one min-reduction per row of 8); the others go to the fix-up queue.  DC-only blocks are
+//    evaluated in the reference's operation order right away.
+//  * phase 1b: fix-up queue, FP64 (exact order when within 1e-9 of an integer)
+//  * phase 1c: the 2048 chroma pairs of the tile -> integer offsets floor((Cr-128)*1.4020), floor(-(Cb-128)*0.3441 -
+//    (Cr-128)*0.7139), floor((Cb-128)*1.7718): trunc(y + t) = y + floor(t) for every value that is not clamped, and the
+//    clamp absorbs the rest (tools/colour_floor_check.py proves this exhaustively); pairs whose G term is within 1.2e-4
+//    of an integer are flagged and take the reference's FP64 expression per pixel
+//  * phase 2: one thread per (row, MCU): 16 pixels, integer adds, saturating packs, three 16-byte planar stores
 // =====================================================================================================
+constexpr int kInvThreads = 192;
 constexpr int kIYStride = 1040;    // bytes per row of the luma sample tile (512 int16 + 16)
 constexpr int kICStride = 528;     // bytes per row of a chroma sample tile (256 int16 + 16)
-constexpr int kInvSmem = kTileBlk * kOutStride + 16 * kIYStride + 2 * 8 * kICStride + kFixCap * 2 + 16;
+constexpr int kInvSmem = kTileBlk * kOutStride + 16 * kIYStride + 2 * 8 * kICStride + kFixCap * 2 + 16 + kTileBlk;
+static_assert(2 * 2048 * 4 <= kTileBlk * kOutStride, "the chroma offset tables reuse the coefficient staging buffer");
 
 // worst-case output error of the FP32 AAN inverse flowgraph per unit of dequantised coefficient, in units of
 // 2^-24 (tools/aan_idct_error_bound.py), natural order, rounded up
@@ -196,6 +214,42 @@ __device__ __forceinline__ void aan_idct8(float& d0, float& d1, float& d2, float
     d2 = e2 + o5, d5 = e2 - o5;
     d4 = e3 + o4, d3 = e3 - o4;
 }
+// the same flowgraph with d3..d7 == 0 (resp. d4..d7 == 0): every operation whose operand is a structural zero is dropped
+// (x + 0, x - 0, 0 * c are exact), so the results equal aan_idct8's bit for bit
+__device__ __forceinline__ void aan_idct8_in3(float& d0, float& d1, float& d2, float& d3, float& d4, float& d5, float& d6, float& d7)
+{
+    const float t12 = fmaf(d2, 1.414213562373095049f, -d2);
+    const float e0 = d0 + d2, e3 = d0 - d2, e1 = d0 + t12, e2 = d0 - t12;
+    const float o7 = d1;
+    const float o11 = d1 * 1.414213562373095049f;
+    const float z5 = d1 * 1.847759065022573512f;
+    const float o10 = fmaf(d1, 1.082392200292393968f, -z5);
+    const float o6 = z5 - o7;
+    const float o5 = o11 - o6;
+    const float o4 = o10 + o5;
+    d0 = e0 + o7, d7 = e0 - o7;
+    d1 = e1 + o6, d6 = e1 - o6;
+    d2 = e2 + o5, d5 = e2 - o5;
+    d4 = e3 + o4, d3 = e3 - o4;
+}
+__device__ __forceinline__ void aan_idct8_in4(float& d0, float& d1, float& d2, float& d3, float& d4, float& d5, float& d6, float& d7)
+{
+    const float t12 = fmaf(d2, 1.414213562373095049f, -d2);
+    const float e0 = d0 + d2, e3 = d0 - d2, e1 = d0 + t12, e2 = d0 - t12;
+    const float dm = d1 - d3;                                   // z11 - z13 == z10 + z12 (z13 = d3, z10 = -d3, z11 = z12 = d1)
+    const float o7 = d1 + d3;
+    const float o11 = dm * 1.414213562373095049f;
+    const float z5 = dm * 1.847759065022573512f;
+    const float o10 = fmaf(d1, 1.082392200292393968f, -z5);
+    const float o12 = fmaf(d3, 2.613125929752753055f, z5);       // (-d3) * (-2.613...) + z5
+    const float o6 = o12 - o7;
+    const float o5 = o11 - o6;
+    const float o4 = o10 + o5;
+    d0 = e0 + o7, d7 = e0 - o7;
+    d1 = e1 + o6, d6 = e1 - o6;
+    d2 = e2 + o5, d5 = e2 - o5;
+    d4 = e3 + o4, d3 = e3 - o4;
+}
 
 // dequantise one 16-byte group (8 zig-zag consecutive coefficients) into the natural-order register array
 template <int COMP, int GRP>
@@ -212,38 +266,53 @@ __device__ __forceinline__ void dequant_group(const InvParams& p, const uint4 ra
     }
 }
 
+// dequantisation + IDCT of one block; `wm` = OR of the non-zero-group masks of the warp's blocks (warp uniform)
 template <int COMP>
-__device__ __forceinline__ void dequant_block(const InvParams& p, const uint4* __restrict__ src, float (&d)[64], float& gsum, bool& dc_only)
+__device__ __forceinline__ void idct_block(const InvParams& p, const uint4* __restrict__ src, const uint4 raw0, const uint32_t wm, float (&d)[64],
+                                           float& gsum)
 {
-    uint4 raw[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) raw[g] = src[g];
-    uint32_t ac = (raw[0].x >> 16) | raw[0].y | raw[0].z | raw[0].w;
-#pragma unroll
-    for (int g = 1; g < 8; ++g) ac |= raw[g].x | raw[g].y | raw[g].z | raw[g].w;
-    dc_only = ac == 0;
     gsum = 2e-5f;
+    if (wm <= 1u) {
+        // only zig-zag positions 0..7 = natural (0,0) (0,1) (1,0) (2,0) (1,1) (0,2) (0,3) (1,2): rows v <= 2, columns u <= 3
+        dequant_group<COMP, 0>(p, raw0, d, gsum);
+        d[11] = d[17] = d[18] = d[19] = 0.0f;
+        d[0] += 128.0f;   // level shift rides on the DC term (gain 1 through the flowgraph)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) aan_idct8_in3(d[u], d[8 + u], d[16 + u], d[24 + u], d[32 + u], d[40 + u], d[48 + u], d[56 + u]);
+#pragma unroll
+        for (int y = 0; y < 8; ++y)
+            aan_idct8_in4(d[y * 8 + 0], d[y * 8 + 1], d[y * 8 + 2], d[y * 8 + 3], d[y * 8 + 4], d[y * 8 + 5], d[y * 8 + 6], d[y * 8 + 7]);
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 64; ++k) d[k] = 0.0f;
-    // group 0 always; the other groups only when some lane of the warp has a non-zero coefficient in them
-    dequant_group<COMP, 0>(p, raw[0], d, gsum);
-    if (__any_sync(0xffffffffu, (raw[1].x | raw[1].y | raw[1].z | raw[1].w) != 0)) dequant_group<COMP, 1>(p, raw[1], d, gsum);
-    if (__any_sync(0xffffffffu, (raw[2].x | raw[2].y | raw[2].z | raw[2].w) != 0)) dequant_group<COMP, 2>(p, raw[2], d, gsum);
-    if (__any_sync(0xffffffffu, (raw[3].x | raw[3].y | raw[3].z | raw[3].w) != 0)) dequant_group<COMP, 3>(p, raw[3], d, gsum);
-    if (__any_sync(0xffffffffu, (raw[4].x | raw[4].y | raw[4].z | raw[4].w) != 0)) dequant_group<COMP, 4>(p, raw[4], d, gsum);
-    if (__any_sync(0xffffffffu, (raw[5].x | raw[5].y | raw[5].z | raw[5].w) != 0)) dequant_group<COMP, 5>(p, raw[5], d, gsum);
-    if (__any_sync(0xffffffffu, (raw[6].x | raw[6].y | raw[6].z | raw[6].w) != 0)) dequant_group<COMP, 6>(p, raw[6], d, gsum);
-    if (__any_sync(0xffffffffu, (raw[7].x | raw[7].y | raw[7].z | raw[7].w) != 0)) dequant_group<COMP, 7>(p, raw[7], d, gsum);
+    dequant_group<COMP, 0>(p, raw0, d, gsum);
+    if (wm & 0x02u) dequant_group<COMP, 1>(p, src[1], d, gsum);
+    if (wm & 0x04u) dequant_group<COMP, 2>(p, src[2], d, gsum);
+    if (wm & 0x08u) dequant_group<COMP, 3>(p, src[3], d, gsum);
+    if (wm & 0x10u) dequant_group<COMP, 4>(p, src[4], d, gsum);
+    if (wm & 0x20u) dequant_group<COMP, 5>(p, src[5], d, gsum);
+    if (wm & 0x40u) dequant_group<COMP, 6>(p, src[6], d, gsum);
+    if (wm & 0x80u) dequant_group<COMP, 7>(p, src[7], d, gsum);
+    d[0] += 128.0f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) aan_idct8(d[u], d[8 + u], d[16 + u], d[24 + u], d[32 + u], d[40 + u], d[48 + u], d[56 + u]);
+#pragma unroll
+    for (int y = 0; y < 8; ++y)
+        aan_idct8(d[y * 8 + 0], d[y * 8 + 1], d[y * 8 + 2], d[y * 8 + 3], d[y * 8 + 4], d[y * 8 + 5], d[y * 8 + 6], d[y * 8 + 7]);
 }
 
-// FP64 re-evaluation of one sample of block `cz` (zig-zag int16 coefficients) with quantiser table qt (natural order)
-__device__ __noinline__ int idct_fix(const int16_t* __restrict__ cz, const uint16_t* __restrict__ qt, int x, int y, uint32_t* exact_hits)
+// FP64 re-evaluation of one sample of block `cz` (zig-zag int16 coefficients, non-zero only below position nlim) with
+// quantiser table qt (natural order)
+__device__ __noinline__ int idct_fix(const int16_t* __restrict__ cz, const uint16_t* __restrict__ qt, int nlim, int x, int y, uint32_t* exact_hits)
 {
     double acc = 0.0;
-    for (int n = 0; n < 64; ++n) {
+    unsigned long long nzmask = 0;
+    for (int n = 0; n < nlim; ++n) {
         const int c = cz[n];
         if (!c) continue;
         const int nat = cC.zz[n], v = nat >> 3, u = nat & 7;
+        nzmask |= 1ull << nat;
         const double f = double(c * int(qt[nat])) * (u ? 1.0 : 0.70710678118654752440) * (v ? 1.0 : 0.70710678118654752440);
         acc = fma(f * cC.cos_ref[u * 8 + x], cC.cos_ref[v * 8 + y], acc);
     }
@@ -251,27 +320,19 @@ __device__ __noinline__ int idct_fix(const int16_t* __restrict__ cz, const uint1
     if (fabs(val - rint(val)) >= 1e-9) return __double2int_rz(val);
     // the reference's exact operation order: natural order ascending, zero terms cannot change the sum
     double sum = 0.0;
-    for (int nat = 0; nat < 64; ++nat) {
-        const int c = cz[cC.izz[nat]];
-        if (!c) continue;
+    while (nzmask) {
+        const int nat = __ffsll((long long)nzmask) - 1;
+        nzmask &= nzmask - 1;
         const int v = nat >> 3, u = nat & 7;
         const double cu = u ? 1.0 : cC.inv_sqrt2_ref, cv = v ? 1.0 : cC.inv_sqrt2_ref;
         double t = __dmul_rn(cu, cv);
-        t = __dmul_rn(t, double(c * int(qt[nat])));
+        t = __dmul_rn(t, double(int(cz[cC.izz[nat]]) * int(qt[nat])));
         t = __dmul_rn(t, cC.cos_ref[u * 8 + x]);
         t = __dmul_rn(t, cC.cos_ref[v * 8 + y]);
         sum = __dadd_rn(sum, t);
     }
     ++*exact_hits;
     return __double2int_rz(__dadd_rn(__dmul_rn(sum, 0.25), 128.0));
-}
-
-constexpr uint32_t kWholeBlock = 1u << 15;   // above the 8-bit block number (blk << 7 occupies bits 7..14)
-
-__device__ __noinline__ void push_fix16(uint32_t* s_nfix, uint16_t* s_fix, uint32_t entry)
-{
-    const uint32_t idx = atomicAdd(s_nfix, 1u);
-    if (idx < kFixCap) s_fix[idx] = uint16_t(entry);
 }
 
 // colour conversion of 4 horizontally adjacent pixels sharing 2 chroma pairs; y4: 4 int16 in two words
@@ -286,22 +347,46 @@ __device__ __noinline__ uint32_t colour_exact4(const int* y, int cb0, int cr0, i
     return out;
 }
 
-__device__ __forceinline__ uint32_t sat_u8(float v)
+constexpr uint32_t kWholeBlock = 1u << 15;   // above the 8-bit block number (blk << 7 occupies bits 7..14)
+
+__device__ __noinline__ void push_fix16(uint32_t* s_nfix, uint16_t* s_fix, uint32_t entry)
 {
-    uint32_t r;
-    asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return r;
+    const uint32_t idx = atomicAdd(s_nfix, 1u);
+    if (idx < kFixCap) s_fix[idx] = uint16_t(entry);
 }
 
-__global__ void __launch_bounds__(256, 2) k_inv_transform(const __grid_constant__ InvParams p)
+// slow half of the guard test of one row: which of the 8 samples are inside the band
+__device__ __noinline__ void flag_row(const float (&v)[8], float guard, uint32_t blk, int y, uint32_t* s_nfix, uint16_t* s_fix)
+{
+#pragma unroll 1
+    for (int x = 0; x < 8; ++x) {
+        const float kf = (v[x] + 12582912.0f) - 12582912.0f;
+        if (fabsf(v[x] - kf) < guard) push_fix16(s_nfix, s_fix, (blk << 7) | uint32_t(y * 8 + x));
+    }
+}
+
+// four s32 -> four saturated u8 in one word (v0 in the low byte): d = (c[15:0] << 16) | sat(a) << 8 | sat(b)
+__device__ __forceinline__ uint32_t pack_sat_u8x4(int v0, int v1, int v2, int v3)
+{
+    uint32_t hi, out;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(v3), "r"(v2));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(v1), "r"(v0), "r"(hi));
+    return out;
+}
+
+__device__ __forceinline__ int sx_lo(uint32_t w) { return int(short(w & 0xffffu)); }   // sign-extended low half (one SGXT / PRMT)
+__device__ __forceinline__ int sx_hi(uint32_t w) { return int(w) >> 16; }
+
+__global__ void __launch_bounds__(kInvThreads, 3) k_inv_transform(const __grid_constant__ InvParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* s_coef = smem;                                  // [192][144] zig-zag int16 coefficients (padded)
+    uint8_t* s_coef = smem;                                  // [192][144] zig-zag int16 coefficients (padded); later the offset tables
     uint8_t* s_y = s_coef + kTileBlk * kOutStride;           // [16][kIYStride] int16 luma samples
     uint8_t* s_cb = s_y + 16 * kIYStride;                    // [8][kICStride]
     uint8_t* s_cr = s_cb + 8 * kICStride;
     uint16_t* s_fix = reinterpret_cast<uint16_t*>(s_cr + 8 * kICStride);
     uint32_t* s_nfix = reinterpret_cast<uint32_t*>(s_fix + kFixCap);
+    uint8_t* s_mask = reinterpret_cast<uint8_t*>(s_nfix) + 16;   // [192] non-zero zig-zag groups of every block
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t mx0 = blockIdx.x * kTileMcu;
@@ -314,56 +399,74 @@ __global__ void __launch_bounds__(256, 2) k_inv_transform(const __grid_constant_
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.coefs + img * p.coef_stride + (size_t(my) * p.HU + mx0) * 384);
         const uint32_t nchunks = nvalid * 48;
-        for (uint32_t c = t; c < kTileBlk * 8; c += 256)
-            *reinterpret_cast<uint4*>(&s_coef[(c >> 3) * kOutStride + (c & 7) * 16]) = c < nchunks ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t c = uint32_t(t) + uint32_t(i) * kInvThreads;
+            const uint4 v = c < nchunks ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(&s_coef[(c >> 3) * kOutStride + (c & 7) * 16]) = v;
+            const uint32_t nzb = __ballot_sync(0xffffffffu, (v.x | v.y | v.z | v.w) != 0u);
+            if ((lane & 7) == 0) s_mask[c >> 3] = uint8_t(nzb >> lane);
+        }
     }
     __syncthreads();
 
     // ---- phase 1: dequantisation + IDCT, one thread per block (warps 0..3 luma, 4 Cb, 5 Cr) ----
-    if (warp < 6) {
+    {
         uint32_t blk;
         uint8_t* tile;
-        int stride;
+        int stride, comp;
         if (warp < 4) {
             const uint32_t mcu = (warp >> 1) * 16 + (lane >> 1), k = (warp & 1) * 2 + (lane & 1);
             blk = mcu * 6 + k;
             tile = &s_y[(warp & 1) * 8 * kIYStride + (mcu * 16 + (lane & 1) * 8) * 2];
-            stride = kIYStride;
+            stride = kIYStride, comp = 0;
         } else {
             blk = lane * 6 + warp;
             tile = (warp == 4 ? s_cb : s_cr) + lane * 16;
-            stride = kICStride;
+            stride = kICStride, comp = warp - 3;
         }
-        float d[64];
-        float gsum;
-        bool dc_only;
+        const uint32_t mask = s_mask[blk];
+        const uint32_t wm = __reduce_or_sync(0xffffffffu, mask);
         const uint4* src = reinterpret_cast<const uint4*>(&s_coef[blk * kOutStride]);
-        if (warp < 4) dequant_block<0>(p, src, d, gsum, dc_only);
-        else if (warp == 4) dequant_block<1>(p, src, d, gsum, dc_only);
-        else dequant_block<2>(p, src, d, gsum, dc_only);
-        d[0] += 128.0f;   // level shift rides on the DC term (gain 1 through the flowgraph)
+        const uint4 raw0 = src[0];
+        const bool dc_only = mask <= 1u && ((raw0.x >> 16) | raw0.y | raw0.z | raw0.w) == 0u;
+        if (__all_sync(0xffffffffu, dc_only)) {
+            // every block of the warp is DC-only: ((c*c)*F)*1*1, /4, +128 exactly as the reference evaluates it
+            const double f = double(int(short(raw0.x & 0xffffu)) * int(p.qt[comp][0]));
+            const double term = __dmul_rn(__dmul_rn(cC.inv_sqrt2_ref, cC.inv_sqrt2_ref), f);
+            const int v = __double2int_rz(__dadd_rn(__dmul_rn(term, 0.25), 128.0));
+            const uint32_t vv = __byte_perm(uint32_t(v), uint32_t(v), 0x5410);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) aan_idct8(d[u], d[8 + u], d[16 + u], d[24 + u], d[32 + u], d[40 + u], d[48 + u], d[56 + u]);
+            for (int y = 0; y < 8; ++y) *reinterpret_cast<uint4*>(tile + y * stride) = make_uint4(vv, vv, vv, vv);
+            if (lane == 0) atomicAdd(p.guard_counter, 32ull * 64ull);
+        } else {
+            float d[64];
+            float gsum;
+            if (warp < 4) idct_block<0>(p, src, raw0, wm, d, gsum);
+            else if (warp == 4) idct_block<1>(p, src, raw0, wm, d, gsum);
+            else idct_block<2>(p, src, raw0, wm, d, gsum);
+            // DC-only blocks: the exact value is very often an integer; the whole block is decided in the fix-up pass
+            const float guard = dc_only ? -1.0f : gsum;
+            if (dc_only) push_fix16(s_nfix, s_fix, (blk << 7) | 64u);
 #pragma unroll
-        for (int y = 0; y < 8; ++y)
-            aan_idct8(d[y * 8 + 0], d[y * 8 + 1], d[y * 8 + 2], d[y * 8 + 3], d[y * 8 + 4], d[y * 8 + 5], d[y * 8 + 6], d[y * 8 + 7]);
-        // DC-only blocks: the exact value is very often an integer; the whole block is decided in the fix-up pass
-        const float guard = dc_only ? -1.0f : gsum;
-        if (dc_only) push_fix16(s_nfix, s_fix, (blk << 7) | 64u);
+            for (int y = 0; y < 8; ++y) {
+                int iv[8];
+                float vr[8];
+                float m = 1.0f;
 #pragma unroll
-        for (int y = 0; y < 8; ++y) {
-            int iv[8];
-#pragma unroll
-            for (int x = 0; x < 8; ++x) {
-                const float val = d[y * 8 + x];
-                iv[x] = __float2int_rz(val);
-                const float kf = (val + 12582912.0f) - 12582912.0f;   // rint(val), |val| < 2^22
-                if (fabsf(val - kf) < guard) push_fix16(s_nfix, s_fix, (blk << 7) | uint32_t(y * 8 + x));
+                for (int x = 0; x < 8; ++x) {
+                    const float val = d[y * 8 + x];
+                    vr[x] = val;
+                    iv[x] = __float2int_rz(val);
+                    const float kf = (val + 12582912.0f) - 12582912.0f;   // rint(val), |val| < 2^22
+                    m = fminf(m, fabsf(val - kf));
+                }
+                if (m < guard) flag_row(vr, guard, blk, y, s_nfix, s_fix);
+                uint4 v;
+                v.x = __byte_perm(uint32_t(iv[0]), uint32_t(iv[1]), 0x5410), v.y = __byte_perm(uint32_t(iv[2]), uint32_t(iv[3]), 0x5410);
+                v.z = __byte_perm(uint32_t(iv[4]), uint32_t(iv[5]), 0x5410), v.w = __byte_perm(uint32_t(iv[6]), uint32_t(iv[7]), 0x5410);
+                *reinterpret_cast<uint4*>(tile + y * stride) = v;
             }
-            uint4 v;
-            v.x = __byte_perm(uint32_t(iv[0]), uint32_t(iv[1]), 0x5410), v.y = __byte_perm(uint32_t(iv[2]), uint32_t(iv[3]), 0x5410);
-            v.z = __byte_perm(uint32_t(iv[4]), uint32_t(iv[5]), 0x5410), v.w = __byte_perm(uint32_t(iv[6]), uint32_t(iv[7]), 0x5410);
-            *reinterpret_cast<uint4*>(tile + y * stride) = v;
         }
     }
     __syncthreads();
@@ -375,13 +478,14 @@ __global__ void __launch_bounds__(256, 2) k_inv_transform(const __grid_constant_
             const bool overflow = nfix > kFixCap;
             uint32_t exact_hits = 0;    // samples decided by the reference's exact operation order (JPEZYB200_STAT_GUARD_INV)
             const uint32_t ntask = overflow ? kTileBlk * 8u : nfix * 8u;
-            for (uint32_t task = t; task < ntask; task += 256) {
+            for (uint32_t task = t; task < ntask; task += kInvThreads) {
                 // entry = blk << 7 | flags: bit 6 = DC-only block, bits 0..5 = sample; kWholeBlock (overflow only) = every sample
                 const uint32_t e = overflow ? (((task >> 3) << 7) | kWholeBlock) : s_fix[task >> 3];
                 const uint32_t blk = (e >> 7) & 255u, sub = task & 7u;
                 const uint32_t mcu = blk / 6u, k = blk - mcu * 6u;
                 const int comp = k < 4u ? 0 : int(k) - 3;
                 const int16_t* cz = reinterpret_cast<const int16_t*>(&s_coef[blk * kOutStride]);
+                const int nlim = 8 * (32 - __clz(uint32_t(s_mask[blk]) | 1u));
                 int16_t* tile;
                 int stride;
                 if (k < 4u) {
@@ -392,7 +496,7 @@ __global__ void __launch_bounds__(256, 2) k_inv_transform(const __grid_constant_
                     stride = kICStride / 2;
                 }
                 if (e & kWholeBlock) {     // overflow path: row `sub` of the block, every sample in FP64
-                    for (int x = 0; x < 8; ++x) tile[sub * stride + x] = int16_t(idct_fix(cz, p.qt[comp], x, int(sub), &exact_hits));
+                    for (int x = 0; x < 8; ++x) tile[sub * stride + x] = int16_t(idct_fix(cz, p.qt[comp], nlim, x, int(sub), &exact_hits));
                 } else if (e & 64u) {      // DC-only block: ((c*c)*F)*1*1, /4, +128 exactly as the reference evaluates it
                     const double f = double(int(cz[0]) * int(p.qt[comp][0]));
                     const double term = __dmul_rn(__dmul_rn(cC.inv_sqrt2_ref, cC.inv_sqrt2_ref), f);
@@ -402,99 +506,95 @@ __global__ void __launch_bounds__(256, 2) k_inv_transform(const __grid_constant_
                     exact_hits += 8;
                 } else if (sub == 0) {
                     const int s = int(e & 63u);
-                    tile[(s >> 3) * stride + (s & 7)] = int16_t(idct_fix(cz, p.qt[comp], s & 7, s >> 3, &exact_hits));
+                    tile[(s >> 3) * stride + (s & 7)] = int16_t(idct_fix(cz, p.qt[comp], nlim, s & 7, s >> 3, &exact_hits));
                 }
             }
             exact_hits = __reduce_add_sync(0xffffffffu, exact_hits);
             if (lane == 0 && exact_hits) atomicAdd(p.guard_counter, (unsigned long long)exact_hits);
-            __syncthreads();
         }
     }
+    __syncthreads();
 
-    // ---- phase 2: chroma replication + colour conversion + planar stores; warp = row pair, lane = MCU ----
-    {
-        const uint32_t mx = mx0 + lane;
-        const uint32_t x0 = mx * 16u;
-        if (mx >= p.HU) return;
-        uint8_t* R = p.r + img * p.plane_stride;
-        uint8_t* G = p.g + img * p.plane_stride;
-        uint8_t* B = p.b + img * p.plane_stride;
-        // 8 chroma pairs of this MCU row pair
-        const uint4 cbw = *reinterpret_cast<const uint4*>(&s_cb[warp * kICStride + lane * 16]);
-        const uint4 crw = *reinterpret_cast<const uint4*>(&s_cr[warp * kICStride + lane * 16]);
-        const uint32_t cbv[4] = {cbw.x, cbw.y, cbw.z, cbw.w}, crv[4] = {crw.x, crw.y, crw.z, crw.w};
-        float tr[8], tg[8], tb[8];
-        int cbi[8], cri[8];
-        uint32_t suspect = 0;
-        if (!p.gray) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                cbi[c] = (c & 1) ? (int(cbv[c >> 1]) >> 16) : int(short(cbv[c >> 1] & 0xffffu));
-                cri[c] = (c & 1) ? (int(crv[c >> 1]) >> 16) : int(short(crv[c >> 1] & 0xffffu));
-                const float a = float(cbi[c] - 128), b = float(cri[c] - 128);
-                tr[c] = b * 1.4020f;
-                tb[c] = a * 1.7718f;
-                tg[c] = fmaf(b, -0.7139f, a * -0.3441f);
-                // G is an exact integer only when 3441a + 7139b = 0 (mod 10000); FP32 error of tg < 7.5e-5 for |a|,|b| <= 256
-                const float kf = (tg[c] + 12582912.0f) - 12582912.0f;
-                const bool near_int = fabsf(tg[c] - kf) < 7.5e-5f && (cbi[c] != 128 || cri[c] != 128);
-                const bool wild = uint32_t(cbi[c] + 128) > 512u || uint32_t(cri[c] + 128) > 512u;
-                if (near_int || wild) suspect |= 1u << c;
-            }
+    // ---- phase 1c: chroma pairs -> integer colour offsets (the coefficient staging buffer is free now) ----
+    uint32_t* s_offa = reinterpret_cast<uint32_t*>(s_coef);            // [8][256]  fr | fg << 16
+    uint32_t* s_offb = s_offa + 2048;                                  // [8][256]  fb | suspect << 16
+    if (!p.gray) {
+#pragma unroll 1
+        for (uint32_t pr = t; pr < 2048u; pr += kInvThreads) {
+            const uint32_t crow = pr >> 8, cx = pr & 255u;
+            const int cb = *reinterpret_cast<const int16_t*>(&s_cb[crow * kICStride + cx * 2]);
+            const int cr = *reinterpret_cast<const int16_t*>(&s_cr[crow * kICStride + cx * 2]);
+            const float a = float(cb - 128), b = float(cr - 128);
+            const int fr = __float2int_rd(b * 1.4020f);
+            const int fb = __float2int_rd(a * 1.7718f);
+            const float tg = fmaf(b, -0.7139f, a * -0.3441f);
+            const int fg = __float2int_rd(tg);
+            // G is an exact integer only when 3441a + 7139b = 0 (mod 10000); FP32 error of tg < 4.5e-5 for |a|,|b| <= 256
+            const float kf = (tg + 12582912.0f) - 12582912.0f;
+            const bool near_int = fabsf(tg - kf) < 7.5e-5f && (cb != 128 || cr != 128);
+            const bool wild = uint32_t(cb + 128) > 512u || uint32_t(cr + 128) > 512u;
+            s_offa[pr] = (uint32_t(fr) & 0xffffu) | (uint32_t(fg) << 16);
+            s_offb[pr] = (uint32_t(fb) & 0xffffu) | ((near_int || wild) ? 0x10000u : 0u);
         }
+        __syncthreads();
+    }
+
+    // ---- phase 2: colour + planar stores; one thread per (row, MCU) ----
+    uint8_t* R = p.r + img * p.plane_stride;
+    uint8_t* G = p.g + img * p.plane_stride;
+    uint8_t* B = p.b + img * p.plane_stride;
+#pragma unroll 1
+    for (uint32_t task = t; task < 512u; task += kInvThreads) {
+        const uint32_t ry = task >> 5, mcu = task & 31u;
+        const uint32_t x0 = (mx0 + mcu) * 16u;
+        if (mx0 + mcu >= p.HU) continue;
+        const uint4 ya = *reinterpret_cast<const uint4*>(&s_y[ry * kIYStride + mcu * 32]);
+        const uint4 yb = *reinterpret_cast<const uint4*>(&s_y[ry * kIYStride + mcu * 32 + 16]);
+        const uint32_t yw[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+        uint32_t ro[4], go[4], bo[4];
+        if (p.gray) {
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            const int ry = warp * 2 + rr;
-            const uint4 ya = *reinterpret_cast<const uint4*>(&s_y[ry * kIYStride + lane * 32]);
-            const uint4 yb = *reinterpret_cast<const uint4*>(&s_y[ry * kIYStride + lane * 32 + 16]);
-            const uint32_t yw[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
-            uint32_t ro[4], go[4], bo[4];
+            for (int q4 = 0; q4 < 4; ++q4)
+                ro[q4] = go[q4] = bo[q4] = pack_sat_u8x4(sx_lo(yw[q4 * 2]), sx_hi(yw[q4 * 2]), sx_lo(yw[q4 * 2 + 1]), sx_hi(yw[q4 * 2 + 1]));
+        } else {
+            const uint32_t obase = (ry >> 1) * 256u + mcu * 8u;
+            const uint4 oa0 = *reinterpret_cast<const uint4*>(&s_offa[obase]), oa1 = *reinterpret_cast<const uint4*>(&s_offa[obase + 4]);
+            const uint4 ob0 = *reinterpret_cast<const uint4*>(&s_offb[obase]), ob1 = *reinterpret_cast<const uint4*>(&s_offb[obase + 4]);
+            const uint32_t oa[8] = {oa0.x, oa0.y, oa0.z, oa0.w, oa1.x, oa1.y, oa1.z, oa1.w};
+            const uint32_t ob[8] = {ob0.x, ob0.y, ob0.z, ob0.w, ob1.x, ob1.y, ob1.z, ob1.w};
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {       // 4 pixels = 2 chroma pairs
-                int yi[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t w = yw[q4 * 2 + (i >> 1)];
-                    yi[i] = (i & 1) ? (int(w) >> 16) : int(short(w & 0xffffu));
-                }
-                if (p.gray) {
-                    uint32_t v = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) v |= sat_u8(float(yi[i])) << (8 * i);
-                    ro[q4] = go[q4] = bo[q4] = v;
+                const int c0 = q4 * 2, c1 = q4 * 2 + 1;
+                const int y0 = sx_lo(yw[c0]), y1 = sx_hi(yw[c0]), y2 = sx_lo(yw[c1]), y3 = sx_hi(yw[c1]);
+                if ((ob[c0] | ob[c1]) & 0x10000u) {
+                    // rare: the reference's FP64 expressions, from the stored chroma samples
+                    const int yi[4] = {y0, y1, y2, y3};
+                    const int16_t* pcb = reinterpret_cast<const int16_t*>(&s_cb[(ry >> 1) * kICStride + (mcu * 8 + c0) * 2]);
+                    const int16_t* pcr = reinterpret_cast<const int16_t*>(&s_cr[(ry >> 1) * kICStride + (mcu * 8 + c0) * 2]);
+                    ro[q4] = colour_exact4(yi, pcb[0], pcr[0], pcb[1], pcr[1], 0);
+                    go[q4] = colour_exact4(yi, pcb[0], pcr[0], pcb[1], pcr[1], 1);
+                    bo[q4] = colour_exact4(yi, pcb[0], pcr[0], pcb[1], pcr[1], 2);
                 } else {
-                    const int c0 = q4 * 2, c1 = q4 * 2 + 1;
-                    if ((suspect >> c0) & 3u) {
-                        ro[q4] = colour_exact4(yi, cbi[c0], cri[c0], cbi[c1], cri[c1], 0);
-                        go[q4] = colour_exact4(yi, cbi[c0], cri[c0], cbi[c1], cri[c1], 1);
-                        bo[q4] = colour_exact4(yi, cbi[c0], cri[c0], cbi[c1], cri[c1], 2);
-                    } else {
-                        uint32_t rv = 0, gv = 0, bv = 0;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float yf = float(yi[i]);
-                            const int c = i < 2 ? c0 : c1;
-                            rv |= sat_u8(yf + tr[c]) << (8 * i);
-                            gv |= sat_u8(yf + tg[c]) << (8 * i);
-                            bv |= sat_u8(yf + tb[c]) << (8 * i);
-                        }
-                        ro[q4] = rv, go[q4] = gv, bo[q4] = bv;
-                    }
+                    const int fr0 = sx_lo(oa[c0]), fg0 = sx_hi(oa[c0]), fb0 = sx_lo(ob[c0]);
+                    const int fr1 = sx_lo(oa[c1]), fg1 = sx_hi(oa[c1]), fb1 = sx_lo(ob[c1]);
+                    ro[q4] = pack_sat_u8x4(y0 + fr0, y1 + fr0, y2 + fr1, y3 + fr1);
+                    go[q4] = pack_sat_u8x4(y0 + fg0, y1 + fg0, y2 + fg1, y3 + fg1);
+                    bo[q4] = pack_sat_u8x4(y0 + fb0, y1 + fb0, y2 + fb1, y3 + fb1);
                 }
             }
-            const size_t rowoff = (size_t(my) * 16 + ry) * p.W;
-            if ((p.W & 15u) == 0 && x0 + 16u <= p.W) {
-                *reinterpret_cast<uint4*>(R + rowoff + x0) = make_uint4(ro[0], ro[1], ro[2], ro[3]);
-                *reinterpret_cast<uint4*>(G + rowoff + x0) = make_uint4(go[0], go[1], go[2], go[3]);
-                *reinterpret_cast<uint4*>(B + rowoff + x0) = make_uint4(bo[0], bo[1], bo[2], bo[3]);
-            } else {
+        }
+        const size_t rowoff = (size_t(my) * 16 + ry) * p.W;
+        if ((p.W & 15u) == 0 && x0 + 16u <= p.W) {
+            *reinterpret_cast<uint4*>(R + rowoff + x0) = make_uint4(ro[0], ro[1], ro[2], ro[3]);
+            *reinterpret_cast<uint4*>(G + rowoff + x0) = make_uint4(go[0], go[1], go[2], go[3]);
+            *reinterpret_cast<uint4*>(B + rowoff + x0) = make_uint4(bo[0], bo[1], bo[2], bo[3]);
+        } else {
 #pragma unroll 1
-                for (int i = 0; i < 16; ++i) {
-                    if (x0 + i >= p.W) break;
-                    R[rowoff + x0 + i] = uint8_t(ro[i >> 2] >> (8 * (i & 3)));
-                    G[rowoff + x0 + i] = uint8_t(go[i >> 2] >> (8 * (i & 3)));
-                    B[rowoff + x0 + i] = uint8_t(bo[i >> 2] >> (8 * (i & 3)));
-                }
+            for (int i = 0; i < 16; ++i) {
+                if (x0 + i >= p.W) break;
+                R[rowoff + x0 + i] = uint8_t(ro[i >> 2] >> (8 * (i & 3)));
+                G[rowoff + x0 + i] = uint8_t(go[i >> 2] >> (8 * (i & 3)));
+                B[rowoff + x0 + i] = uint8_t(bo[i >> 2] >> (8 * (i & 3)));
             }
         }
     }
