@@ -442,36 +442,47 @@ __global__ void __launch_bounds__(kInvThreads, 3) k_inv_transform(const __grid_c
         } else {
             float d[64];
             float gsum;
+            uint32_t dc_exact = 0;
             if (warp < 4) idct_block<0>(p, src, raw0, wm, d, gsum);
             else if (warp == 4) idct_block<1>(p, src, raw0, wm, d, gsum);
             else idct_block<2>(p, src, raw0, wm, d, gsum);
-            // DC-only blocks: the exact value is very often an integer; the whole block is decided in the fix-up pass
-            const float guard = dc_only ? -1.0f : gsum;
-            if (dc_only) push_fix16(s_nfix, s_fix, (blk << 7) | 64u);
+            if (dc_only) {
+                // the exact value is very often an integer: ((c*c)*F)*1*1, /4, +128 exactly as the reference evaluates it
+                const double f = double(int(short(raw0.x & 0xffffu)) * int(p.qt[comp][0]));
+                const double term = __dmul_rn(__dmul_rn(cC.inv_sqrt2_ref, cC.inv_sqrt2_ref), f);
+                const int v = __double2int_rz(__dadd_rn(__dmul_rn(term, 0.25), 128.0));
+                const uint32_t vv = __byte_perm(uint32_t(v), uint32_t(v), 0x5410);
 #pragma unroll
-            for (int y = 0; y < 8; ++y) {
-                int iv[8];
-                float vr[8];
-                float m = 1.0f;
+                for (int y = 0; y < 8; ++y) *reinterpret_cast<uint4*>(tile + y * stride) = make_uint4(vv, vv, vv, vv);
+                dc_exact = 64;
+            } else {
 #pragma unroll
-                for (int x = 0; x < 8; ++x) {
-                    const float val = d[y * 8 + x];
-                    vr[x] = val;
-                    iv[x] = __float2int_rz(val);
-                    const float kf = (val + 12582912.0f) - 12582912.0f;   // rint(val), |val| < 2^22
-                    m = fminf(m, fabsf(val - kf));
+                for (int y = 0; y < 8; ++y) {
+                    int iv[8];
+                    float vr[8];
+                    float m = 1.0f;
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) {
+                        const float val = d[y * 8 + x];
+                        vr[x] = val;
+                        iv[x] = __float2int_rz(val);
+                        const float kf = (val + 12582912.0f) - 12582912.0f;   // rint(val), |val| < 2^22
+                        m = fminf(m, fabsf(val - kf));
+                    }
+                    if (m < gsum) flag_row(vr, gsum, blk, y, s_nfix, s_fix);
+                    uint4 v;
+                    v.x = __byte_perm(uint32_t(iv[0]), uint32_t(iv[1]), 0x5410), v.y = __byte_perm(uint32_t(iv[2]), uint32_t(iv[3]), 0x5410);
+                    v.z = __byte_perm(uint32_t(iv[4]), uint32_t(iv[5]), 0x5410), v.w = __byte_perm(uint32_t(iv[6]), uint32_t(iv[7]), 0x5410);
+                    *reinterpret_cast<uint4*>(tile + y * stride) = v;
                 }
-                if (m < guard) flag_row(vr, guard, blk, y, s_nfix, s_fix);
-                uint4 v;
-                v.x = __byte_perm(uint32_t(iv[0]), uint32_t(iv[1]), 0x5410), v.y = __byte_perm(uint32_t(iv[2]), uint32_t(iv[3]), 0x5410);
-                v.z = __byte_perm(uint32_t(iv[4]), uint32_t(iv[5]), 0x5410), v.w = __byte_perm(uint32_t(iv[6]), uint32_t(iv[7]), 0x5410);
-                *reinterpret_cast<uint4*>(tile + y * stride) = v;
             }
+            dc_exact = __reduce_add_sync(0xffffffffu, dc_exact);
+            if (lane == 0 && dc_exact) atomicAdd(p.guard_counter, (unsigned long long)dc_exact);
         }
     }
     __syncthreads();
 
-    // ---- phase 1b: dense re-evaluation of the queue (guard-band samples and DC-only blocks) ----
+    // ---- phase 1b: dense re-evaluation of the queue (guard-band samples) ----
     {
         const uint32_t nfix = *s_nfix;
         if (nfix) {
@@ -479,7 +490,7 @@ __global__ void __launch_bounds__(kInvThreads, 3) k_inv_transform(const __grid_c
             uint32_t exact_hits = 0;    // samples decided by the reference's exact operation order (JPEZYB200_STAT_GUARD_INV)
             const uint32_t ntask = overflow ? kTileBlk * 8u : nfix * 8u;
             for (uint32_t task = t; task < ntask; task += kInvThreads) {
-                // entry = blk << 7 | flags: bit 6 = DC-only block, bits 0..5 = sample; kWholeBlock (overflow only) = every sample
+                // entry = blk << 7 | sample; kWholeBlock (overflow only) = every sample of the block
                 const uint32_t e = overflow ? (((task >> 3) << 7) | kWholeBlock) : s_fix[task >> 3];
                 const uint32_t blk = (e >> 7) & 255u, sub = task & 7u;
                 const uint32_t mcu = blk / 6u, k = blk - mcu * 6u;
@@ -497,13 +508,6 @@ __global__ void __launch_bounds__(kInvThreads, 3) k_inv_transform(const __grid_c
                 }
                 if (e & kWholeBlock) {     // overflow path: row `sub` of the block, every sample in FP64
                     for (int x = 0; x < 8; ++x) tile[sub * stride + x] = int16_t(idct_fix(cz, p.qt[comp], nlim, x, int(sub), &exact_hits));
-                } else if (e & 64u) {      // DC-only block: ((c*c)*F)*1*1, /4, +128 exactly as the reference evaluates it
-                    const double f = double(int(cz[0]) * int(p.qt[comp][0]));
-                    const double term = __dmul_rn(__dmul_rn(cC.inv_sqrt2_ref, cC.inv_sqrt2_ref), f);
-                    const int v = __double2int_rz(__dadd_rn(__dmul_rn(term, 0.25), 128.0));
-                    const uint32_t vv = __byte_perm(uint32_t(v), uint32_t(v), 0x5410);
-                    *reinterpret_cast<uint4*>(tile + sub * stride) = make_uint4(vv, vv, vv, vv);
-                    exact_hits += 8;
                 } else if (sub == 0) {
                     const int s = int(e & 63u);
                     tile[(s >> 3) * stride + (s & 7)] = int16_t(idct_fix(cz, p.qt[comp], nlim, s & 7, s >> 3, &exact_hits));
@@ -520,21 +524,28 @@ __global__ void __launch_bounds__(kInvThreads, 3) k_inv_transform(const __grid_c
     uint32_t* s_offb = s_offa + 2048;                                  // [8][256]  fb | suspect << 16
     if (!p.gray) {
 #pragma unroll 1
-        for (uint32_t pr = t; pr < 2048u; pr += kInvThreads) {
-            const uint32_t crow = pr >> 8, cx = pr & 255u;
-            const int cb = *reinterpret_cast<const int16_t*>(&s_cb[crow * kICStride + cx * 2]);
-            const int cr = *reinterpret_cast<const int16_t*>(&s_cr[crow * kICStride + cx * 2]);
-            const float a = float(cb - 128), b = float(cr - 128);
-            const int fr = __float2int_rd(b * 1.4020f);
-            const int fb = __float2int_rd(a * 1.7718f);
-            const float tg = fmaf(b, -0.7139f, a * -0.3441f);
-            const int fg = __float2int_rd(tg);
-            // G is an exact integer only when 3441a + 7139b = 0 (mod 10000); FP32 error of tg < 4.5e-5 for |a|,|b| <= 256
-            const float kf = (tg + 12582912.0f) - 12582912.0f;
-            const bool near_int = fabsf(tg - kf) < 7.5e-5f && (cb != 128 || cr != 128);
-            const bool wild = uint32_t(cb + 128) > 512u || uint32_t(cr + 128) > 512u;
-            s_offa[pr] = (uint32_t(fr) & 0xffffu) | (uint32_t(fg) << 16);
-            s_offb[pr] = (uint32_t(fb) & 0xffffu) | ((near_int || wild) ? 0x10000u : 0u);
+        for (uint32_t pp = t; pp < 1024u; pp += kInvThreads) {     // two horizontally adjacent pairs per iteration
+            const uint32_t crow = pp >> 7, cx2 = pp & 127u;
+            const uint32_t cbw = *reinterpret_cast<const uint32_t*>(&s_cb[crow * kICStride + cx2 * 4]);
+            const uint32_t crw = *reinterpret_cast<const uint32_t*>(&s_cr[crow * kICStride + cx2 * 4]);
+            uint32_t oa[2], ob[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int cb = h ? sx_hi(cbw) : sx_lo(cbw), cr = h ? sx_hi(crw) : sx_lo(crw);
+                const float a = float(cb - 128), b = float(cr - 128);
+                const int fr = __float2int_rd(b * 1.4020f);
+                const int fb = __float2int_rd(a * 1.7718f);
+                const float tg = fmaf(b, -0.7139f, a * -0.3441f);
+                const int fg = __float2int_rd(tg);
+                // G is an exact integer only when 3441a + 7139b = 0 (mod 10000); FP32 error of tg < 4.5e-5 for |a|,|b| <= 256
+                const float kf = (tg + 12582912.0f) - 12582912.0f;
+                const bool near_int = fabsf(tg - kf) < 7.5e-5f && ((cb ^ 128) | (cr ^ 128)) != 0;
+                const bool wild = (uint32_t(cb + 128) | uint32_t(cr + 128)) > 512u;   // (conservative: OR of two values <= 512)
+                oa[h] = __byte_perm(uint32_t(fr), uint32_t(fg), 0x5410);
+                ob[h] = (uint32_t(fb) & 0xffffu) | ((near_int || wild) ? 0x10000u : 0u);
+            }
+            *reinterpret_cast<uint2*>(&s_offa[pp * 2]) = make_uint2(oa[0], oa[1]);
+            *reinterpret_cast<uint2*>(&s_offb[pp * 2]) = make_uint2(ob[0], ob[1]);
         }
         __syncthreads();
     }
