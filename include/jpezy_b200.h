@@ -65,8 +65,8 @@ enum {
                                      guard band + exact recompute (default), 1 = FP64 separable
                                      (validation build)                                           */
     JPEZYB200_OPT_SYNC_ROUNDS = 3 /* self-synchronisation launches enqueued after the first one by the
-                                     decoder: n > 0 = exactly n, no host round trip (default 4; two are
-                                     needed on ordinary streams, later ones return at once); 0 = the
+                                     decoder: n > 0 = exactly n, no host round trip (default 3; one is
+                                     needed on ordinary streams thanks to the warm-up overlap, later ones return at once); 0 = the
                                      host polls a device flag after every launch until the fixed point */
 };
 JPEZYB200_API int jpezyb200_set_option(jpezyb200_ctx* ctx, int option, int64_t value);
@@ -76,7 +76,9 @@ enum {
     JPEZYB200_STAT_KERNEL_LAUNCHES = 1,  /* number of kernels this library launched              */
     JPEZYB200_STAT_GUARD_FWD = 2,        /* DCT coefficients re-computed in exact reference order */
     JPEZYB200_STAT_GUARD_INV = 3,        /* IDCT samples re-computed in exact reference order     */
-    JPEZYB200_STAT_SYNC_ROUNDS = 4       /* self-synchronisation rounds of the last decode        */
+    JPEZYB200_STAT_SYNC_ROUNDS = 4,      /* self-synchronisation rounds of the last decode        */
+    JPEZYB200_STAT_SYNC_ITERS0 = 5,      /* last decode: most shared-memory iterations any CTA needed in launch 0 */
+    JPEZYB200_STAT_SYNC_ITERS1 = 6       /* ... and in launch 1 (= synchronisation distance in subsequences)      */
 };
 JPEZYB200_API int jpezyb200_get_stat(jpezyb200_ctx* ctx, int stat, uint64_t* value);
 

@@ -8,7 +8,7 @@ _LIB = None
 
 OK, EINVAL, ECAPACITY, ECUDA, ENCCL, ECORRUPT, ENODEVICE, ENOMEM, EUNSUPPORTED, EAGAIN = range(10)
 OPT_PAD_ONES, OPT_TRANSFORM, OPT_SYNC_ROUNDS = 1, 2, 3
-STAT_KERNEL_LAUNCHES, STAT_GUARD_FWD, STAT_GUARD_INV, STAT_SYNC_ROUNDS = 1, 2, 3, 4
+STAT_KERNEL_LAUNCHES, STAT_GUARD_FWD, STAT_GUARD_INV, STAT_SYNC_ROUNDS, STAT_SYNC_ITERS0, STAT_SYNC_ITERS1 = 1, 2, 3, 4, 5, 6
 
 EXPORTS = [
     "jpezyb200_abi_version", "jpezyb200_ctx_create", "jpezyb200_ctx_destroy", "jpezyb200_strerror", "jpezyb200_last_error",

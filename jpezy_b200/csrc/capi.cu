@@ -184,7 +184,8 @@ int jpezyb200_get_stat(jpezyb200_ctx* ctx, int stat, uint64_t* value)
         *value = ctx->launches;
         return JPEZYB200_OK;
     }
-    int idx = stat == JPEZYB200_STAT_GUARD_FWD ? 0 : stat == JPEZYB200_STAT_GUARD_INV ? 1 : stat == JPEZYB200_STAT_SYNC_ROUNDS ? 2 : -1;
+    int idx = stat == JPEZYB200_STAT_GUARD_FWD ? 0 : stat == JPEZYB200_STAT_GUARD_INV ? 1 : stat == JPEZYB200_STAT_SYNC_ROUNDS ? 2 :
+              stat == JPEZYB200_STAT_SYNC_ITERS0 ? 4 : stat == JPEZYB200_STAT_SYNC_ITERS1 ? 5 : -1;
     if (idx < 0) return ctx->fail(JPEZYB200_EINVAL, "unknown stat");
     JZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     unsigned long long v = 0;

@@ -60,7 +60,7 @@ struct jpezyb200_ctx {
     std::string err;
     int pad_ones = 1;
     int transform_variant = 0;
-    int sync_rounds = 4;
+    int sync_rounds = 3;
     uint64_t launches = 0;
     bool inv_attr_set = false;
 

@@ -26,12 +26,23 @@ constexpr int kDecThreads = 256;
 constexpr int kLutBits = 10;
 
 // compact canonical decoder table for one DHT table, built on the host
-struct HuffDecTab {
-    uint16_t fast[1 << kLutBits];  // peek kLutBits bits -> len | size << 5 | run << 9, 0 = longer than kLutBits / invalid
+// entry of the decoder tables: (len + size) | len << 5 | size << 10 | run << 14   (size / run = low / high nibble of the symbol);
+// 0 = no code of at most kLutBits bits starts here
+__host__ __device__ inline uint32_t huff_entry(uint32_t len, uint32_t sym)
+{
+    return (len + (sym & 15u)) | (len << 5) | ((sym & 15u) << 10) | ((sym >> 4) << 14);
+}
+struct HuffSlow {                  // codes longer than kLutBits
     int32_t maxcode[18];           // maxcode[len] (left-aligned compare uses plain codes), -1 = none
     int32_t valptr[17];            // index into vals of the first code of this length minus its code
+    int32_t pad_;                  // keeps sizeof(HuffDecTab) a multiple of 16
     uint8_t vals[256];
 };
+struct HuffDecTab {
+    uint32_t fast[1 << kLutBits];  // indexed by the next kLutBits bits
+    HuffSlow slow;
+};
+static_assert(sizeof(HuffSlow) % 4 == 0 && sizeof(HuffDecTab) % 16 == 0, "copied to shared memory in words / 16-byte chunks");
 
 struct DecParams {
     // geometry
@@ -49,7 +60,7 @@ struct DecParams {
     uint64_t* chunk_base;     // [nimg][nchunk]
     uint64_t* ubytes;         // [nimg] un-stuffed byte count
     // synchronisation
-    uint32_t sub_bits;        // subsequence length in bits (power of two >= 128)
+    uint32_t sub_bits;        // subsequence length in bits (128, 256 or 512)
     uint32_t nsub;            // subsequences per image (capacity)
     uint32_t* sub_state;      // [nimg][nsub] packed end state of every subsequence
     uint32_t* state_a;        // [nimg][ncta] CTA tail states, double buffered across launches
@@ -59,6 +70,7 @@ struct DecParams {
     uint32_t rounds;          // launches 1..rounds of k_sync_decode are enqueued after launch 0
     uint32_t rounds_host;     // launches the host-driven loop needed (rounds == 0)
     unsigned long long* rounds_stat;   // receives the number of launches that did work
+    unsigned long long* iters_stat;    // [2] max / sum over CTAs of the shared-memory iterations of launch 0
     // tables: [0]=DC sel by comp class 0, [1]=DC class 1, [2]=AC class 0, [3]=AC class 1
     const HuffDecTab* tabs;
     // output
@@ -77,18 +89,24 @@ __device__ __forceinline__ uint32_t pack_state(uint32_t over, uint32_t b, uint32
 }
 constexpr uint32_t kStateSyncMask = (1u << 15) - 1u;   // (overshoot, b, z)
 
-// ---- bit reader over the un-stuffed stream (big-endian bit order), 64-bit register buffer ------------
+// ---- bit reader over the CTA's span of the un-stuffed stream, staged in shared memory ---------------------
+// The span holds the CTA's kDecThreads subsequences plus kSpanSlack bytes of look-ahead, as raw bytes (big-endian
+// bit order); positions are bits relative to the span start.  The word after the buffered ones is always
+// pre-loaded, so that a refill costs two shifts and no shared-memory latency on the critical path.
+constexpr int kSpanSlack = 64;
 struct BitBuf {
-    const uint32_t* w;   // next word to load
+    const uint32_t* w;   // next word to pre-load (shared memory)
     uint64_t buf;        // left-aligned
+    uint32_t nxt;        // pre-loaded, byte-swapped word that follows the buffered bits
     int n;               // valid bits in buf
-    uint64_t pos;        // absolute bit position of the first bit of buf
-    __device__ __forceinline__ void init(const uint8_t* base, uint64_t p)
+    uint32_t pos;        // bit position of the first bit of buf, relative to the span
+    __device__ __forceinline__ void init(const uint32_t* span, uint32_t p)
     {
-        w = reinterpret_cast<const uint32_t*>(base) + (p >> 5);
-        const uint32_t a = __byte_perm(__ldg(w), 0, 0x0123), b = __byte_perm(__ldg(w + 1), 0, 0x0123);
-        w += 2;
-        const uint32_t sh = uint32_t(p & 31u);
+        w = span + (p >> 5);
+        const uint32_t a = __byte_perm(w[0], 0, 0x0123), b = __byte_perm(w[1], 0, 0x0123);
+        nxt = __byte_perm(w[2], 0, 0x0123);
+        w += 3;
+        const uint32_t sh = p & 31u;
         buf = ((uint64_t(a) << 32) | b) << sh;
         n = 64 - int(sh);
         pos = p;
@@ -96,82 +114,100 @@ struct BitBuf {
     __device__ __forceinline__ void refill()   // guarantees n >= 32
     {
         if (n < 32) {
-            buf |= uint64_t(__byte_perm(__ldg(w++), 0, 0x0123)) << (32 - n);
+            buf |= uint64_t(nxt) << (32 - n);
             n += 32;
+            nxt = __byte_perm(*w++, 0, 0x0123);
         }
     }
     __device__ __forceinline__ uint32_t peek32() const { return uint32_t(buf >> 32); }
     __device__ __forceinline__ void skip(int k) { buf <<= k; n -= k; pos += k; }
 };
 
-__device__ __forceinline__ uint32_t huff_lookup(const HuffDecTab* __restrict__ t, const uint16_t* __restrict__ s_fast, uint32_t bits32)
+__device__ __noinline__ uint32_t huff_lookup_slow(const HuffSlow* __restrict__ t, uint32_t bits32)
 {
-    // returns len | size << 5 | run << 9 (size = low nibble of the symbol, run = high nibble), 0 when no code matches
-    const uint32_t e = s_fast[bits32 >> (32 - kLutBits)];
-    if (e) return e;
 #pragma unroll 1
     for (int len = kLutBits + 1; len <= 16; ++len) {
         const int32_t code = int32_t(bits32 >> (32 - len));
-        if (code <= t->maxcode[len]) {
-            const uint32_t sym = t->vals[(code + t->valptr[len]) & 255];
-            return uint32_t(len) | ((sym & 15u) << 5) | ((sym >> 4) << 9);
-        }
+        if (code <= t->maxcode[len]) return huff_entry(uint32_t(len), t->vals[(code + t->valptr[len]) & 255]);
     }
     return 0;
 }
 
-// Decode from (br.pos, b, z) until br.pos >= end (or >= limit).  With kWrite the coefficients that carry a value
-// field are stored (the buffer is pre-zeroed), block ordinals start at blk.
+// Decode from (br.pos, b, z) until br.pos >= end (or >= limit); positions are relative to the span.  With kWrite the
+// coefficients that carry a value field are stored (the buffer is pre-zeroed), block ordinals start at blk.
+// s_fast: [0] = DC class 0 (luma), [1] = DC class 1, [2] = AC class 0, [3] = AC class 1
 template <bool kWrite>
-__device__ __forceinline__ void decode_span(BitBuf& br, uint32_t& b, uint32_t& z, uint32_t& nblocks, const uint64_t end,
-                                            const uint64_t limit, const HuffDecTab* __restrict__ tabs,
-                                            const uint16_t (*s_fast)[1 << kLutBits], int16_t* __restrict__ out, uint64_t blk,
+__device__ __forceinline__ void decode_span(BitBuf& br, uint32_t& b, uint32_t& z, uint32_t& nblocks, const uint32_t end,
+                                            const uint32_t limit, const HuffSlow* __restrict__ slow,
+                                            const uint32_t (*s_fast)[1 << kLutBits], int16_t* __restrict__ out, uint64_t blk,
                                             const uint64_t nblk, int* corrupt)
 {
-    const uint64_t stop = end < limit ? end : limit;
+    const uint32_t stop = end < limit ? end : limit;
+    uint32_t ti = (z == 0 ? 0u : 2u) + (b >= 4u ? 1u : 0u);
     while (br.pos < stop) {
         br.refill();
-        const int ti = (z == 0 ? 0 : 2) + (b >= 4 ? 1 : 0);
         const uint32_t w = br.peek32();
-        const uint32_t e = huff_lookup(tabs + ti, s_fast[ti], w);
-        if (e == 0) {              // no such code: only legal while speculating
-            if (kWrite && corrupt) *corrupt = 1;
-            br.skip(1);
-            continue;
+        uint32_t e = s_fast[ti][w >> (32 - kLutBits)];
+        if (e == 0) {
+            e = huff_lookup_slow(slow + ti, w);
+            if (e == 0) {          // no such code: only legal while speculating
+                if (kWrite && corrupt) *corrupt = 1;
+                br.skip(1);
+                continue;
+            }
         }
-        const uint32_t len = e & 31u, s = (e >> 5) & 15u;
-        const uint32_t run = (z == 0) ? 0u : (e >> 9);
-        br.skip(int(len + s));     // len + s <= 31 and the buffer holds >= 32 bits
-        if (z != 0 && (e >> 5) == 0) {   // EOB (run = size = 0)
+        br.skip(int(e & 31u));     // code + value field <= 31 bits and the buffer holds >= 32
+        const uint32_t rs = e >> 10;               // size | run << 4
+        const uint32_t zin = z;
+        if (zin != 0u && rs == 0u) {               // EOB
             z = 64;
         } else {
-            z += run;
-            if (z > 63) {          // run past the end of the block (src/decoder/jpezy_decoder.hpp:619)
+            z += (zin == 0u) ? 0u : (rs >> 4);
+            if (z > 63u) {         // run past the end of the block (src/decoder/jpezy_decoder.hpp:619)
                 if (kWrite && corrupt) *corrupt = 1;
                 z = 64;
             } else {
-                if (kWrite && s && blk < nblk) {
-                    const uint32_t vbits = (w << len) >> (32 - s);
-                    int v = int(vbits);
-                    if (!(vbits & (1u << (s - 1)))) v -= (1 << s) - 1;
-                    out[blk * 64 + z] = int16_t(v);
+                if (kWrite) {
+                    const uint32_t len = (e >> 5) & 31u, s = rs & 15u;
+                    if (s && blk < nblk) {
+                        const uint32_t vbits = (w << len) >> (32 - s);
+                        int v = int(vbits);
+                        if (!(vbits & (1u << (s - 1)))) v -= (1 << s) - 1;
+                        out[blk * 64 + z] = int16_t(v);
+                    }
                 }
                 z += 1;
             }
         }
-        if (z >= 64) {
+        if (z >= 64u) {
             z = 0;
-            b = (b == 5) ? 0 : b + 1;
+            b = (b == 5u) ? 0u : b + 1u;
             ++nblocks;
             ++blk;
             if (kWrite && blk >= nblk) return;
         }
+        ti = (z == 0u ? 0u : 2u) + (b >= 4u ? 1u : 0u);
     }
 }
 
-__device__ __forceinline__ void load_dec_tabs(const HuffDecTab* __restrict__ tabs, uint16_t (*s_fast)[1 << kLutBits])
+__device__ __forceinline__ void load_dec_tabs(const HuffDecTab* __restrict__ tabs, uint32_t (*s_fast)[1 << kLutBits], HuffSlow* s_slow)
 {
-    for (int i = threadIdx.x; i < 4 * (1 << kLutBits); i += blockDim.x) s_fast[i >> kLutBits][i & ((1 << kLutBits) - 1)] = tabs[i >> kLutBits].fast[i & ((1 << kLutBits) - 1)];
+    constexpr int kFast16 = (1 << kLutBits) * 4 / 16, kSlowW = int(sizeof(HuffSlow) / 4);
+    for (int i = threadIdx.x; i < 4 * kFast16; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_fast[i / kFast16])[i % kFast16] = __ldg(reinterpret_cast<const uint4*>(tabs[i / kFast16].fast) + i % kFast16);
+    for (int i = threadIdx.x; i < 4 * kSlowW; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(&s_slow[i / kSlowW])[i % kSlowW] = __ldg(reinterpret_cast<const uint32_t*>(&tabs[i / kSlowW].slow) + i % kSlowW);
+}
+
+// stage the CTA's span of the un-stuffed stream: bytes [byte0, byte0 + span_bytes + kSpanSlack), 16-byte chunks
+// (the stream buffer carries >= 128 bytes of zero slack behind the data and its slots are 16-byte aligned)
+__device__ __forceinline__ void load_span(const uint8_t* __restrict__ ustream, uint64_t byte0, uint32_t span_bytes, uint64_t uslot, uint32_t* s_span)
+{
+    const uint4* src = reinterpret_cast<const uint4*>(ustream + byte0);
+    uint4* dst = reinterpret_cast<uint4*>(s_span);
+    const uint32_t n16 = (span_bytes + kSpanSlack) / 16;
+    const uint64_t avail16 = (uslot - byte0) / 16;        // the last CTA's span reaches past the image's slot: zeros there
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = i < avail16 ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
 }
 
 // ---- D0: un-stuffing -------------------------------------------------------------------------------
@@ -282,30 +318,47 @@ __global__ void __launch_bounds__(kDecThreads) k_unstuff_write(const DecParams p
 }
 
 // ---- D1a: speculative decode + synchronisation --------------------------------------------------------
-// One CTA owns kDecThreads consecutive subsequences.  Launch 0: every thread decodes its subsequence from the
-// guessed state (b = 0, z = 0); then the CTA iterates in shared memory: a thread whose predecessor's end state
-// changed re-decodes from it, until nothing changes inside the CTA.  Only the first thread of a CTA depends on
-// another CTA (the previous CTA's last end state, `tail`); later launches re-seed it from the previous launch's
-// tails and re-propagate.  `changed` counts the end states that changed during a launch; 0 = global fixed point.
+// One CTA owns kDecOwn consecutive subsequences and, in launch 0, also decodes the kDecWarm subsequences in front of
+// them (which belong to the previous CTA) as a warm-up.  Launch 0: every thread decodes its subsequence from the guessed
+// state (b = 0, z = 0); then the CTA iterates in shared memory: a thread whose predecessor's end state changed
+// re-decodes from it, until nothing changes inside the CTA.  Huffman codes re-synchronise within a few subsequences, so
+// by the end of the warm-up run the states are the true ones and the owned subsequences come out right in launch 0.
+// Launch k >= 1: the first owned subsequence is re-seeded from the previous CTA's last end state of launch k - 1
+// (`tail`); `changed` counts the end states that changed during a launch, 0 = global fixed point (normally launch 1).
+constexpr int kDecWarm = 32;
+constexpr int kDecOwn = kDecThreads - kDecWarm;
+
 __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, const int launch, const int host_poll)
 {
-    __shared__ uint16_t s_fast[4][1 << kLutBits];
+    extern __shared__ __align__(16) uint32_t s_span[];      // (kDecThreads * sub_bits / 8 + kSpanSlack) bytes of the stream
+    __shared__ __align__(16) uint32_t s_fast[4][1 << kLutBits];
+    __shared__ __align__(16) HuffSlow s_slow[4];
     __shared__ uint32_t s_state[kDecThreads];
     __shared__ uint8_t s_chg[2][kDecThreads];
     // launches are enqueued without host round trips: once a launch saw no change (a global fixed point), the
     // later ones return immediately (changed[] stays 0 for them, so the zero propagates to changed[rounds])
     // (host_poll: the host reads changed[1] after every launch instead)
     if (!host_poll && launch >= 2 && p.changed[launch - 1] == 0) return;
-    load_dec_tabs(p.tabs, s_fast);
     const size_t img = blockIdx.y;
     const uint64_t total_bits = p.ubytes[img] * 8;
     const int t = threadIdx.x;
-    const uint32_t i = blockIdx.x * kDecThreads + t;
-    const uint64_t start = uint64_t(i) * p.sub_bits;
-    const bool valid = start < total_bits && i < p.nsub;
-    const uint64_t end = start + p.sub_bits;
-    const size_t si = img * p.nsub + i;
-    const uint8_t* base = p.ustream + img * p.uslot;
+    const uint32_t first_own = blockIdx.x * kDecOwn;                                   // first owned subsequence
+    const uint32_t first = blockIdx.x == 0 ? 0u : first_own - kDecWarm;                // first subsequence of the span
+    const int64_t isub = int64_t(first_own) - kDecWarm + t;                            // this thread's subsequence
+    if (uint64_t(first_own) * p.sub_bits >= total_bits) {     // (capacity CTA beyond the data of this image)
+        if (t == 0) p.sub_blk[img * gridDim.x + blockIdx.x] = 0;
+        return;
+    }
+    const uint64_t span_start = uint64_t(first) * p.sub_bits;                          // multiple of 128 bits
+    const uint32_t span_bits = kDecThreads * p.sub_bits;
+    load_dec_tabs(p.tabs, s_fast, s_slow);
+    load_span(p.ustream + img * p.uslot, span_start / 8, span_bits / 8, p.uslot, s_span);
+    const uint32_t start = uint32_t(isub - int64_t(first)) * p.sub_bits, end = start + p.sub_bits;   // relative to the span
+    const uint32_t limit = uint32_t(min(total_bits - span_start, uint64_t(span_bits) + 256u));
+    const bool owner = t >= kDecWarm;
+    // warm-up threads only work in launch 0; afterwards the owned states are re-seeded from the previous CTA's tail
+    const bool valid = isub >= 0 && isub < int64_t(p.nsub) && start < limit && (owner || launch == 0);
+    const size_t si = img * p.nsub + size_t(isub < 0 ? 0 : isub);
     const uint32_t ncta = gridDim.x;
     const uint32_t* tail_in = (launch & 1) ? p.state_b : p.state_a;     // [nimg][ncta] tails of the previous launch
     uint32_t* tail_out = (launch & 1) ? p.state_a : p.state_b;
@@ -316,20 +369,20 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     if (valid) {
         if (launch == 0) {
             BitBuf br;
-            br.init(base, start);
+            br.init(s_span, start);
             uint32_t b = 0, z = 0, n = 0;
-            decode_span<false>(br, b, z, n, end, total_bits, p.tabs, s_fast, nullptr, 0, 0, nullptr);
-            st = pack_state(uint32_t(br.pos > end ? br.pos - end : 0), b, z, n);
+            decode_span<false>(br, b, z, n, end, limit, s_slow, s_fast, nullptr, 0, 0, nullptr);
+            st = pack_state(br.pos > end ? br.pos - end : 0u, b, z, n);
             chg = true;
         } else {
             st = p.sub_state[si];
-            if (t == 0 && blockIdx.x > 0) {
+            if (t == kDecWarm && blockIdx.x > 0) {
                 const uint32_t ps = tail_in[img * ncta + blockIdx.x - 1];
                 BitBuf br;
-                br.init(base, start + (ps & 63u));
+                br.init(s_span, start + (ps & 63u));
                 uint32_t b = (ps >> 6) & 7u, z = (ps >> 9) & 63u, n = 0;
-                decode_span<false>(br, b, z, n, end, total_bits, p.tabs, s_fast, nullptr, 0, 0, nullptr);
-                const uint32_t ns = pack_state(uint32_t(br.pos > end ? br.pos - end : 0), b, z, n);
+                decode_span<false>(br, b, z, n, end, limit, s_slow, s_fast, nullptr, 0, 0, nullptr);
+                const uint32_t ns = pack_state(br.pos > end ? br.pos - end : 0u, b, z, n);
                 chg = ((ns ^ st) & kStateSyncMask) != 0;
                 st = ns;
             }
@@ -340,34 +393,37 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     uint32_t nchanged = (launch > 0 && chg) ? 1u : 0u;
     __syncthreads();
     for (int it = 0; it < 4 * kDecThreads; ++it) {
-        const bool redo = valid && t > 0 && s_chg[it & 1][t - 1];
+        // (the very first subsequence of the image has no predecessor: its guessed state is the true one)
+        const bool redo = valid && isub > 0 && t > 0 && s_chg[it & 1][t - 1];
         const uint32_t ps = redo ? s_state[t - 1] : 0u;
         bool c2 = false;
         if (redo) {
             BitBuf br;
-            br.init(base, start + (ps & 63u));
+            br.init(s_span, start + (ps & 63u));
             uint32_t b = (ps >> 6) & 7u, z = (ps >> 9) & 63u, n = 0;
-            decode_span<false>(br, b, z, n, end, total_bits, p.tabs, s_fast, nullptr, 0, 0, nullptr);
-            const uint32_t ns = pack_state(uint32_t(br.pos > end ? br.pos - end : 0), b, z, n);
+            decode_span<false>(br, b, z, n, end, limit, s_slow, s_fast, nullptr, 0, 0, nullptr);
+            const uint32_t ns = pack_state(br.pos > end ? br.pos - end : 0u, b, z, n);
             c2 = ((ns ^ st) & kStateSyncMask) != 0;
             st = ns;
         }
         __syncthreads();                 // all reads of s_state[t-1] are done
         if (redo) s_state[t] = st;
         s_chg[(it + 1) & 1][t] = c2 ? 1 : 0;
-        if (c2) ++nchanged;
-        if (!__syncthreads_or(c2 ? 1 : 0)) break;
+        if (c2 && owner) ++nchanged;
+        if (!__syncthreads_or(c2 ? 1 : 0)) {
+            if (t == 0 && launch <= 1) atomicMax(p.iters_stat + launch, (unsigned long long)(it + 1));
+            break;
+        }
     }
-    if (valid) p.sub_state[si] = st;
+    const bool mine = valid && owner;
+    if (mine) p.sub_state[si] = st;
     // the CTA's last valid subsequence is the seed of the next CTA
-    const uint64_t last_start = uint64_t(blockIdx.x * kDecThreads + kDecThreads - 1) * p.sub_bits;
-    const bool is_tail = valid && (t == kDecThreads - 1 || start + p.sub_bits >= total_bits || i + 1 >= p.nsub);
-    (void)last_start;
+    const bool is_tail = mine && (t == kDecThreads - 1 || end >= limit || isub + 1 >= int64_t(p.nsub));
     if (is_tail) tail_out[img * ncta + blockIdx.x] = st;
     if (launch > 0 && nchanged) atomicAdd(p.changed + (host_poll ? 1 : launch), (unsigned long long)nchanged);
-    // blocks completed inside this CTA's subsequences (input of the block-index scan)
+    // blocks completed inside this CTA's own subsequences (input of the block-index scan)
     uint32_t total;
-    cta_scan_excl(valid ? (st >> 15) & 4095u : 0u, reinterpret_cast<uint32_t*>(s_state), &total);
+    cta_scan_excl(mine ? (st >> 15) & 4095u : 0u, reinterpret_cast<uint32_t*>(s_state), &total);
     if (t == 0) p.sub_blk[img * ncta + blockIdx.x] = total;
 }
 
@@ -379,7 +435,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const DecParams p, const u
     const size_t img = blockIdx.x;
     const uint64_t total_bits = p.ubytes[img] * 8;
     const uint32_t nsub = uint32_t(min(uint64_t(p.nsub), (total_bits + p.sub_bits - 1) / p.sub_bits));
-    const uint32_t n = (nsub + kDecThreads - 1) / kDecThreads;
+    const uint32_t n = (nsub + kDecOwn - 1) / kDecOwn;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     for (uint32_t c0 = 0; c0 < n; c0 += 1024) {
@@ -408,29 +464,38 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const DecParams p, const u
 // ---- D1c: final pass, writes the non-zero coefficients (buffer pre-zeroed) ------------------------------
 __global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p)
 {
-    __shared__ uint16_t s_fast[4][1 << kLutBits];
+    extern __shared__ __align__(16) uint32_t s_span[];
+    __shared__ __align__(16) uint32_t s_fast[4][1 << kLutBits];
+    __shared__ __align__(16) HuffSlow s_slow[4];
     __shared__ uint32_t s_warp[kDecThreads / 32];
-    load_dec_tabs(p.tabs, s_fast);
     const size_t img = blockIdx.y;
     const uint64_t total_bits = p.ubytes[img] * 8;
-    const uint32_t i = blockIdx.x * kDecThreads + threadIdx.x;
-    const uint64_t start = uint64_t(i) * p.sub_bits;
-    const bool valid = start < total_bits && i < p.nsub;
+    // same ownership as k_sync_decode (kDecOwn subsequences per CTA; the last kDecWarm threads idle)
+    const uint64_t cta_start = uint64_t(blockIdx.x) * kDecOwn * p.sub_bits;
+    if (cta_start >= total_bits) return;
+    const uint32_t span_bits = kDecOwn * p.sub_bits;
+    load_dec_tabs(p.tabs, s_fast, s_slow);
+    load_span(p.ustream + img * p.uslot, cta_start / 8, span_bits / 8, p.uslot, s_span);
+    const uint32_t i = blockIdx.x * kDecOwn + threadIdx.x;
+    const uint32_t start = threadIdx.x * p.sub_bits;
+    const uint32_t limit = uint32_t(min(total_bits - cta_start, uint64_t(span_bits) + 256u));
+    const bool valid = threadIdx.x < kDecOwn && start < limit && i < p.nsub;
     const size_t si = img * p.nsub + i;
     const uint32_t mine = valid ? p.sub_state[si] : 0u;
+    __syncthreads();
     uint32_t total;
     const uint64_t blk = uint64_t(p.sub_blk[img * gridDim.x + blockIdx.x]) + cta_scan_excl((mine >> 15) & 4095u, s_warp, &total);
     if (!valid || blk >= p.nblk) return;
-    uint64_t pos = start;
+    uint32_t pos = start;
     uint32_t b = 0, z = 0, n = 0;
     if (i) {
         const uint32_t ps = p.sub_state[si - 1];
         pos = start + (ps & 63u), b = (ps >> 6) & 7u, z = (ps >> 9) & 63u;
     }
     BitBuf br;
-    br.init(p.ustream + img * p.uslot, pos);
+    br.init(s_span, pos);
     int corrupt = 0;
-    decode_span<true>(br, b, z, n, start + p.sub_bits, total_bits, p.tabs, s_fast, p.coefs + img * p.coef_stride, blk, p.nblk, &corrupt);
+    decode_span<true>(br, b, z, n, start + p.sub_bits, limit, s_slow, s_fast, p.coefs + img * p.coef_stride, blk, p.nblk, &corrupt);
     if (corrupt && p.status) p.status[img] = JPEZYB200_ECORRUPT;
 }
 

@@ -170,16 +170,19 @@ def test_sync_round_modes_agree(ctx, oracle):
     want = oracle.decode_coefs(f)
     _, _, R0, G0, B0 = oracle.decode(f)
     try:
-        for rounds in (4, 0, 1):
+        for rounds in (3, 0, 1):
             ctx.set_option(capi.OPT_SYNC_ROUNDS, rounds)
             got, st = gpu_entropy_decode(ctx, [split(f)], W, H)
             if rounds == 1:
-                # one re-seeding launch always changes some end states: the device-resident API says "again"
-                assert st[0] == capi.EAGAIN
+                # a single verification launch: either it found the fixed point (the warm-up overlap usually gets the
+                # states right in launch 0) or the device-resident API says "again" -- never a wrong result
+                assert st[0] in (0, capi.EAGAIN)
+                if st[0] == 0:
+                    assert (got[0] == want).all()
             else:
                 assert st[0] == 0 and (got[0] == want).all()
                 assert ctx.stat(capi.STAT_SYNC_ROUNDS) >= 2
             R, G, B = ctx.decode(split(f), J.default_frame(W, H))      # host entry point: always completes
             assert (R == R0).all() and (G == G0).all() and (B == B0).all()
     finally:
-        ctx.set_option(capi.OPT_SYNC_ROUNDS, 4)
+        ctx.set_option(capi.OPT_SYNC_ROUNDS, 3)
