@@ -26,11 +26,17 @@ constexpr int kDecThreads = 256;
 constexpr int kLutBits = 10;
 
 // compact canonical decoder table for one DHT table, built on the host
-// entry of the decoder tables: (len + size) | len << 5 | size << 10 | run << 14   (size / run = low / high nibble of the symbol);
-// 0 = no code of at most kLutBits bits starts here
-__host__ __device__ inline uint32_t huff_entry(uint32_t len, uint32_t sym)
+// entry of the decoder tables (0 = no code of at most kLutBits bits starts here):
+//   bits 0..4   code length + size of the value field = bits to consume
+//   bits 8..14  dz: advance of the zig-zag index; DC tables: 1; AC tables: run + 1, end-of-block: 64 (so that z + dz >= 64
+//               closes the block in both cases; ZRL = (15, 0) advances by 16 like the generic path of the reference,
+//               src/decoder/jpezy_decoder.hpp:611-622)
+//   bits 16..20 code length, bits 21..24 size (value extraction in the writing pass)
+__host__ __device__ inline uint32_t huff_entry(uint32_t len, uint32_t sym, bool ac)
 {
-    return (len + (sym & 15u)) | (len << 5) | ((sym & 15u) << 10) | ((sym >> 4) << 14);
+    const uint32_t size = sym & 15u, run = sym >> 4;
+    const uint32_t dz = !ac ? 1u : (sym == 0u ? 64u : run + 1u);
+    return (len + size) | (dz << 8) | (len << 16) | (size << 21);
 }
 struct HuffSlow {                  // codes longer than kLutBits
     int32_t maxcode[18];           // maxcode[len] (left-aligned compare uses plain codes), -1 = none
@@ -40,7 +46,7 @@ struct HuffSlow {                  // codes longer than kLutBits
 };
 struct HuffDecTab {
     uint32_t fast[1 << kLutBits];  // indexed by the next kLutBits bits
-    HuffSlow slow;
+    HuffSlow slow;                 // slow.pad_ = 1 for AC tables
 };
 static_assert(sizeof(HuffSlow) % 4 == 0 && sizeof(HuffDecTab) % 16 == 0, "copied to shared memory in words / 16-byte chunks");
 
@@ -128,14 +134,14 @@ __device__ __noinline__ uint32_t huff_lookup_slow(const HuffSlow* __restrict__ t
 #pragma unroll 1
     for (int len = kLutBits + 1; len <= 16; ++len) {
         const int32_t code = int32_t(bits32 >> (32 - len));
-        if (code <= t->maxcode[len]) return huff_entry(uint32_t(len), t->vals[(code + t->valptr[len]) & 255]);
+        if (code <= t->maxcode[len]) return huff_entry(uint32_t(len), t->vals[(code + t->valptr[len]) & 255], t->pad_ != 0);
     }
     return 0;
 }
 
 // Decode from (br.pos, b, z) until br.pos >= end (or >= limit); positions are relative to the span.  With kWrite the
 // coefficients that carry a value field are stored (the buffer is pre-zeroed), block ordinals start at blk.
-// s_fast: [0] = DC class 0 (luma), [1] = DC class 1, [2] = AC class 0, [3] = AC class 1
+// s_fast: [0] = DC class 0 (luma), [1] = DC class 1, [2] = AC class 0, [3] = AC class 1 (contiguous)
 template <bool kWrite>
 __device__ __forceinline__ void decode_span(BitBuf& br, uint32_t& b, uint32_t& z, uint32_t& nblocks, const uint32_t end,
                                             const uint32_t limit, const HuffSlow* __restrict__ slow,
@@ -143,50 +149,44 @@ __device__ __forceinline__ void decode_span(BitBuf& br, uint32_t& b, uint32_t& z
                                             const uint64_t nblk, int* corrupt)
 {
     const uint32_t stop = end < limit ? end : limit;
-    uint32_t ti = (z == 0 ? 0u : 2u) + (b >= 4u ? 1u : 0u);
+    // table of the next symbol: DC table of the block's class at z == 0, else the AC table of the same class
+    uint32_t ti = (z == 0u ? 0u : 2u) + (b >= 4u ? 1u : 0u);
     while (br.pos < stop) {
         br.refill();
         const uint32_t w = br.peek32();
         uint32_t e = s_fast[ti][w >> (32 - kLutBits)];
-        if (e == 0) {
+        if (e == 0u) {
             e = huff_lookup_slow(slow + ti, w);
-            if (e == 0) {          // no such code: only legal while speculating
+            if (e == 0u) {         // no such code: only legal while speculating
                 if (kWrite && corrupt) *corrupt = 1;
                 br.skip(1);
                 continue;
             }
         }
         br.skip(int(e & 31u));     // code + value field <= 31 bits and the buffer holds >= 32
-        const uint32_t rs = e >> 10;               // size | run << 4
-        const uint32_t zin = z;
-        if (zin != 0u && rs == 0u) {               // EOB
-            z = 64;
-        } else {
-            z += (zin == 0u) ? 0u : (rs >> 4);
-            if (z > 63u) {         // run past the end of the block (src/decoder/jpezy_decoder.hpp:619)
-                if (kWrite && corrupt) *corrupt = 1;
-                z = 64;
-            } else {
-                if (kWrite) {
-                    const uint32_t len = (e >> 5) & 31u, s = rs & 15u;
-                    if (s && blk < nblk) {
-                        const uint32_t vbits = (w << len) >> (32 - s);
-                        int v = int(vbits);
-                        if (!(vbits & (1u << (s - 1)))) v -= (1 << s) - 1;
-                        out[blk * 64 + z] = int16_t(v);
-                    }
-                }
-                z += 1;
+        const uint32_t dz = (e >> 8) & 127u;
+        if (kWrite) {
+            const uint32_t len = (e >> 16) & 31u, sz = e >> 21;
+            const uint32_t k = z + dz - 1u;                    // zig-zag index of this coefficient
+            if (k > 63u && dz != 64u) {                        // run past the end of the block (src/decoder/jpezy_decoder.hpp:619)
+                if (corrupt) *corrupt = 1;
+            } else if (sz && blk < nblk) {
+                const uint32_t vbits = (w << len) >> (32 - sz);
+                int v = int(vbits);
+                if (!(vbits & (1u << (sz - 1)))) v -= (1 << sz) - 1;
+                out[blk * 64 + k] = int16_t(v);
             }
         }
+        z += dz;
+        ti |= 2u;                  // after the DC symbol: the AC table of the same class
         if (z >= 64u) {
             z = 0;
             b = (b == 5u) ? 0u : b + 1u;
             ++nblocks;
             ++blk;
             if (kWrite && blk >= nblk) return;
+            ti = b >= 4u ? 1u : 0u;
         }
-        ti = (z == 0u ? 0u : 2u) + (b >= 4u ? 1u : 0u);
     }
 }
 

@@ -29,7 +29,7 @@ def main():
         if hdr is None or len(r) <= iI or not r[0].isdigit() or not r[iI].isdigit():
             continue
         per[int(r[0])][0] += int(r[iI])
-        per[int(r[0])][1] += int(r[iS] or 0)
+        per[int(r[0])][1] += int(r[iS]) if r[iS].isdigit() else 0
     tot = sum(v[0] for v in per.values())
     tots = sum(v[1] for v in per.values()) or 1
     print("total warp-instructions %d  = %.1f thread-slots per pixel" % (tot, tot * 32 / npx))
@@ -46,7 +46,7 @@ def main():
         print("%-42s %9d %5.1f%%  slots/px %6.2f  stall-samples %5.1f%%" % (k, n, 100 * n / tot, n * 32 / npx, 100 * s / tots))
     print("hottest lines:")
     for ln, (n, s) in sorted(per.items(), key=lambda kv: -kv[1][0])[:30]:
-        print("%5d %9d %4.1f%% samp %4.1f%% | %s" % (ln, n, 100 * n / tot, 100 * s / tots, src[ln - 1].strip()[:105]))
+        print("%5d %9d %4.1f%% samp %4.1f%% | %s" % (ln, n, 100 * n / tot, 100 * s / tots, src[ln - 1].strip()[:105] if ln <= len(src) else "?"))
 
 
 if __name__ == "__main__":
