@@ -39,6 +39,8 @@ struct ShardParams {
     int pad_ones;                // fill bits of the very last byte (JPEZYB200_OPT_PAD_ONES)
     ShardGeom* geom;
     uint64_t* out_bytes;         // this rank's owned + stuffed byte count (all-gather #3 input)
+    uint8_t* stage;              // local staging of this rank's stuffed bytes, same 16-byte phase as their place in dst
+    size_t stage_cap;
     uint8_t* dst;                // stitched output (possibly on a peer GPU)
     size_t dst_cap;
     uint64_t* total_bytes;       // optional: sum over all ranks (written by every rank, same value)
@@ -160,13 +162,17 @@ __global__ void __launch_bounds__(kStuffThreads) k_shard_stuff_write(const Shard
         if (j < p.rank) byte_base += p.all_bytes[j];
         total += p.all_bytes[j];
     }
+    const uint64_t mine = p.all_bytes[p.rank];
+    const bool ok = g.fits && total <= p.dst_cap && mine + 32 <= p.stage_cap;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (p.total_bytes) *p.total_bytes = total;
-        if (total > p.dst_cap) *p.overflow = 1;
+        if (!ok) *p.overflow = 1;
     }
-    if (!g.fits || total > p.dst_cap) return;
+    if (!ok) return;
     const uint32_t nch = uint32_t((g.nown + kStuffChunk - 1) / kStuffChunk);
-    uint8_t* dst = p.dst + byte_base;
+    // the stuffed bytes are first written locally (byte stores), at the same position modulo 16 as in the stitched
+    // stream, so that k_shard_push can move them to the (possibly remote) destination with aligned 16-byte stores
+    uint8_t* dst = p.stage + (byte_base & 15u);
     for (uint32_t ch = blockIdx.x; ch < nch; ch += gridDim.x) {
         const uint64_t i0 = (uint64_t(ch) * kStuffThreads + threadIdx.x) * 16;
         uint8_t b[16];
@@ -187,6 +193,29 @@ __global__ void __launch_bounds__(kStuffThreads) k_shard_stuff_write(const Shard
             dst[o++] = b[i];
             if (b[i] == 0xffu) dst[o++] = 0;
         }
+    }
+}
+
+// local staging -> this rank's place in the stitched stream: aligned 16-byte loads and stores (peer stores over NVLink
+// when dst lives on another GPU), single bytes only at the two ragged ends
+__global__ void __launch_bounds__(256) k_shard_push(const ShardParams p)
+{
+    if (*p.overflow) return;
+    uint64_t byte_base = 0;
+    for (uint32_t j = 0; j < p.rank; ++j) byte_base += p.all_bytes[j];
+    const uint64_t n = p.all_bytes[p.rank];
+    const uint32_t ph = uint32_t(byte_base & 15u);
+    const uint8_t* src = p.stage;                 // byte i of this rank's segment is at src[ph + i]
+    uint8_t* dst = p.dst + (byte_base - ph);      // 16-byte aligned (dst itself is): byte i goes to dst[ph + i]
+    const uint64_t lo = ph, hi = ph + n;          // [lo, hi) in staging coordinates
+    const uint64_t a0 = (lo + 15) & ~uint64_t(15), a1 = hi & ~uint64_t(15);
+    const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, nth = uint64_t(gridDim.x) * blockDim.x;
+    if (a0 < a1) {
+        for (uint64_t c = a0 / 16 + tid; c < a1 / 16; c += nth) reinterpret_cast<uint4*>(dst)[c] = reinterpret_cast<const uint4*>(src)[c];
+        for (uint64_t i = lo + tid; i < a0; i += nth) dst[i] = src[i];
+        for (uint64_t i = a1 + tid; i < hi; i += nth) dst[i] = src[i];
+    } else {
+        for (uint64_t i = lo + tid; i < hi; i += nth) dst[i] = src[i];
     }
 }
 
