@@ -53,14 +53,25 @@ __device__ __forceinline__ long long prev_same_component(uint32_t b)
     return (long long)b - (k == 0 ? 3 : 6);
 }
 
+// the 64 coefficients of one block: eight 16-byte loads issued back to back (one exposed memory latency, not eight)
+struct BlockRegs {
+    int4 q[8];
+    __device__ __forceinline__ void load(const int16_t* __restrict__ c)
+    {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = __ldg(reinterpret_cast<const int4*>(c) + i);
+    }
+    __device__ __forceinline__ int dc() const { return int(short(q[0].x & 0xffff)); }
+};
+
 // Visit the code words of one block in stream order.  emit(bits, nbits), nbits <= 27.
 template <class Emit>
-__device__ __forceinline__ void encode_block(const int16_t* __restrict__ c, int dc_pred, const uint32_t* __restrict__ ac,
+__device__ __forceinline__ void encode_block(const BlockRegs& blk, int dc_pred, const uint32_t* __restrict__ ac,
                                              const uint32_t* __restrict__ dc, Emit&& emit)
 {
     // DC (:180-191)
     {
-        const int diff = int(c[0]) - dc_pred;
+        const int diff = blk.dc() - dc_pred;
         const int cat = bit_length(abs(diff));
         const uint32_t e = dc[cat];
         const uint32_t vbits = uint32_t(diff < 0 ? diff - 1 : diff) & ((1u << cat) - 1u);
@@ -69,9 +80,9 @@ __device__ __forceinline__ void encode_block(const int16_t* __restrict__ c, int 
     // AC (:194-224)
     int run = 0;
     const uint32_t zrl = ac[0xf0], eob = ac[0x00];
-#pragma unroll 1
+#pragma unroll
     for (int n8 = 0; n8 < 8; ++n8) {
-        const int4 q = *reinterpret_cast<const int4*>(c + n8 * 8);
+        const int4 q = blk.q[n8];
         if (n8 && (q.x | q.y | q.z | q.w) == 0) { run += 8; continue; }
         const int w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -135,8 +146,10 @@ __global__ void __launch_bounds__(kEntThreads) k_block_bits(const EntParams p)
         const long long pb = prev_same_component(b);
         const int cls = (b % 6u) >= 4;
         const int comp = (b % 6u) < 4 ? 0 : int(b % 6u) - 3;
-        const int pred = pb >= 0 ? int(base[size_t(pb) * 64]) : (p.dc_init ? p.dc_init[img * 3 + comp] : 0);
-        encode_block(base + size_t(b) * 64, pred, s_ac[cls], s_dc[cls], [&](uint32_t, int n) { bits += uint32_t(n); });
+        BlockRegs blk;
+        blk.load(base + size_t(b) * 64);
+        const int pred = pb >= 0 ? int(__ldg(base + size_t(pb) * 64)) : (p.dc_init ? p.dc_init[img * 3 + comp] : 0);
+        encode_block(blk, pred, s_ac[cls], s_dc[cls], [&](uint32_t, int n) { bits += uint32_t(n); });
     }
     uint32_t total;
     const uint32_t off = block_scan_excl(bits, s_warp, &total);
@@ -197,7 +210,9 @@ __global__ void __launch_bounds__(kEntThreads) k_scatter(const EntParams p)
     const long long pb = prev_same_component(b);
     const int cls = (b % 6u) >= 4;
     const int comp = (b % 6u) < 4 ? 0 : int(b % 6u) - 3;
-    const int pred = pb >= 0 ? int(base[size_t(pb) * 64]) : (p.dc_init ? p.dc_init[img * 3 + comp] : 0);
+    BlockRegs blk;
+    blk.load(base + size_t(b) * 64);
+    const int pred = pb >= 0 ? int(__ldg(base + size_t(pb) * 64)) : (p.dc_init ? p.dc_init[img * 3 + comp] : 0);
     const uint64_t pos = p.tile_base[img * p.ntile + blockIdx.x] + p.blk_off[img * p.nblk + b];
     uint32_t* out = reinterpret_cast<uint32_t*>(p.ustream + img * p.uslot) + (pos >> 5);
     uint64_t acc = 0;
@@ -215,7 +230,7 @@ __global__ void __launch_bounds__(kEntThreads) k_scatter(const EntParams p)
             acc &= (1ull << n) - 1ull;
         }
     };
-    encode_block(base + size_t(b) * 64, pred, s_ac[cls], s_dc[cls], emit);
+    encode_block(blk, pred, s_ac[cls], s_dc[cls], emit);
     if (b == p.nblk - 1 && p.pad_ones) {   // complete the last byte with 1-bits (write_eoi)
         const int padn = int((8u - uint32_t(total & 7u)) & 7u);
         if (padn) emit((1u << padn) - 1u, padn);
