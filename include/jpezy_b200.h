@@ -133,8 +133,9 @@ typedef struct jpezyb200_huff {
 typedef struct jpezyb200_frame {
     uint32_t width, height;        /* SOF0 (src/decoder/jpezy_decoder.hpp:286-289)                    */
     uint8_t sample_precision;      /* 8                                                               */
-    uint8_t ncomp;                 /* 3 (1 is parsed by the host but not decoded on the device yet)   */
-    uint8_t hs[3], vs[3], tq[3];   /* Frame_component H, V, Tq (src/decoder/tables.hpp:18-21)         */
+    uint8_t ncomp;                 /* 1 or 3                                                          */
+    uint8_t hs[3], vs[3], tq[3];   /* Frame_component H, V, Tq (src/decoder/tables.hpp:18-21); on the
+                                      device: luma H, V in {1, 2}, chroma 1x1                         */
     uint8_t td[3], ta[3];          /* Scan_component Td, Ta (:23-26); the reference uses Td for both  */
     uint16_t restart_interval;     /* DRI (src/decoder/jpezy_decoder.hpp:400-404); must be 0          */
     uint16_t qt[4][64];            /* natural order, as analyze_dqt stores them (:258-277)            */

@@ -54,6 +54,8 @@ struct DecParams {
     // geometry
     uint32_t nblk;            // blocks per image
     uint32_t nmcu;
+    uint32_t nb;              // blocks per MCU (sum of H*V over the components: 1, 3, 4 or 6)
+    uint32_t ny;              // of which luma (component 0); the others are one block each and use the class-1 tables
     // stuffed input
     const uint8_t* scan;      // [nimg][slot]
     size_t slot;
@@ -146,11 +148,11 @@ template <bool kWrite>
 __device__ __forceinline__ void decode_span(BitBuf& br, uint32_t& b, uint32_t& z, uint32_t& nblocks, const uint32_t end,
                                             const uint32_t limit, const HuffSlow* __restrict__ slow,
                                             const uint32_t (*s_fast)[1 << kLutBits], int16_t* __restrict__ out, uint64_t blk,
-                                            const uint64_t nblk, int* corrupt)
+                                            const uint64_t nblk, int* corrupt, const uint32_t nb, const uint32_t ny)
 {
     const uint32_t stop = end < limit ? end : limit;
     // table of the next symbol: DC table of the block's class at z == 0, else the AC table of the same class
-    uint32_t ti = (z == 0u ? 0u : 2u) + (b >= 4u ? 1u : 0u);
+    uint32_t ti = (z == 0u ? 0u : 2u) + (b >= ny ? 1u : 0u);
     while (br.pos < stop) {
         br.refill();
         const uint32_t w = br.peek32();
@@ -181,11 +183,11 @@ __device__ __forceinline__ void decode_span(BitBuf& br, uint32_t& b, uint32_t& z
         ti |= 2u;                  // after the DC symbol: the AC table of the same class
         if (z >= 64u) {
             z = 0;
-            b = (b == 5u) ? 0u : b + 1u;
+            b = (b + 1u == nb) ? 0u : b + 1u;
             ++nblocks;
             ++blk;
             if (kWrite && blk >= nblk) return;
-            ti = b >= 4u ? 1u : 0u;
+            ti = b >= ny ? 1u : 0u;
         }
     }
 }
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
             BitBuf br;
             br.init(s_span, start);
             uint32_t b = 0, z = 0, n = 0;
-            decode_span<false>(br, b, z, n, end, limit, s_slow, s_fast, nullptr, 0, 0, nullptr);
+            decode_span<false>(br, b, z, n, end, limit, s_slow, s_fast, nullptr, 0, 0, nullptr, p.nb, p.ny);
             st = pack_state(br.pos > end ? br.pos - end : 0u, b, z, n);
             chg = true;
         } else {
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
                 BitBuf br;
                 br.init(s_span, start + (ps & 63u));
                 uint32_t b = (ps >> 6) & 7u, z = (ps >> 9) & 63u, n = 0;
-                decode_span<false>(br, b, z, n, end, limit, s_slow, s_fast, nullptr, 0, 0, nullptr);
+                decode_span<false>(br, b, z, n, end, limit, s_slow, s_fast, nullptr, 0, 0, nullptr, p.nb, p.ny);
                 const uint32_t ns = pack_state(br.pos > end ? br.pos - end : 0u, b, z, n);
                 chg = ((ns ^ st) & kStateSyncMask) != 0;
                 st = ns;
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
             BitBuf br;
             br.init(s_span, start + (ps & 63u));
             uint32_t b = (ps >> 6) & 7u, z = (ps >> 9) & 63u, n = 0;
-            decode_span<false>(br, b, z, n, end, limit, s_slow, s_fast, nullptr, 0, 0, nullptr);
+            decode_span<false>(br, b, z, n, end, limit, s_slow, s_fast, nullptr, 0, 0, nullptr, p.nb, p.ny);
             const uint32_t ns = pack_state(br.pos > end ? br.pos - end : 0u, b, z, n);
             c2 = ((ns ^ st) & kStateSyncMask) != 0;
             st = ns;
@@ -495,12 +497,12 @@ __global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p)
     BitBuf br;
     br.init(s_span, pos);
     int corrupt = 0;
-    decode_span<true>(br, b, z, n, start + p.sub_bits, limit, s_slow, s_fast, p.coefs + img * p.coef_stride, blk, p.nblk, &corrupt);
+    decode_span<true>(br, b, z, n, start + p.sub_bits, limit, s_slow, s_fast, p.coefs + img * p.coef_stride, blk, p.nblk, &corrupt, p.nb, p.ny);
     if (corrupt && p.status) p.status[img] = JPEZYB200_ECORRUPT;
 }
 
 // ---- D1d: DC differences -> absolute DC (pred_dct[sc] += diff, src/decoder/jpezy_decoder.hpp:596-597) -----
-// tile = 256 MCUs; per tile the sums of the Y (4 blocks), Cb, Cr differences
+// tile = 256 MCUs; per tile the sums of the Y (ny blocks per MCU), Cb, Cr differences
 __global__ void __launch_bounds__(256) k_dc_sum(const DecParams p)
 {
     __shared__ int s_red[3][8];
@@ -508,9 +510,9 @@ __global__ void __launch_bounds__(256) k_dc_sum(const DecParams p)
     const uint32_t m = blockIdx.x * 256 + threadIdx.x;
     int y = 0, cb = 0, cr = 0;
     if (m < p.nmcu) {
-        const int16_t* c = p.coefs + img * p.coef_stride + size_t(m) * 384;
-        y = int(c[0]) + int(c[64]) + int(c[128]) + int(c[192]);
-        cb = c[256], cr = c[320];
+        const int16_t* c = p.coefs + img * p.coef_stride + size_t(m) * p.nb * 64;
+        for (uint32_t k = 0; k < p.ny; ++k) y += int(c[k * 64]);
+        if (p.nb > p.ny) cb = c[p.ny * 64], cr = c[(p.ny + 1) * 64];
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -552,13 +554,14 @@ __global__ void __launch_bounds__(256) k_dc_apply(const DecParams p)
     __shared__ int s_w[3][8];
     const size_t img = blockIdx.y;
     const uint32_t m = blockIdx.x * 256 + threadIdx.x;
-    int16_t* c = p.coefs + img * p.coef_stride + size_t(min(m, p.nmcu - 1)) * 384;
+    int16_t* c = p.coefs + img * p.coef_stride + size_t(min(m, p.nmcu - 1)) * p.nb * 64;
     int d[6] = {0, 0, 0, 0, 0, 0};
     if (m < p.nmcu) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) d[k] = c[k * 64];
+        for (uint32_t k = 0; k < p.nb; ++k) d[k] = c[k * 64];
     }
-    int v[3] = {d[0] + d[1] + d[2] + d[3], d[4], d[5]};
+    int v[3] = {0, 0, 0};
+    for (uint32_t k = 0; k < p.ny; ++k) v[0] += d[k];
+    if (p.nb > p.ny) v[1] = d[p.ny], v[2] = d[p.ny + 1];
     int incl[3];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -581,12 +584,14 @@ __global__ void __launch_bounds__(256) k_dc_apply(const DecParams p)
         incl[k] += base;   // inclusive prefix up to and including this MCU
     }
     int py = incl[0] - v[0];   // predictor before this MCU
-    py += d[0]; c[0] = int16_t(py);
-    py += d[1]; c[64] = int16_t(py);
-    py += d[2]; c[128] = int16_t(py);
-    py += d[3]; c[192] = int16_t(py);
-    c[256] = int16_t(incl[1]);
-    c[320] = int16_t(incl[2]);
+    for (uint32_t k = 0; k < p.ny; ++k) {
+        py += d[k];
+        c[k * 64] = int16_t(py);
+    }
+    if (p.nb > p.ny) {
+        c[p.ny * 64] = int16_t(incl[1]);
+        c[(p.ny + 1) * 64] = int16_t(incl[2]);
+    }
 }
 
 }  // namespace jz

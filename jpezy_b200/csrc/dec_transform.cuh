@@ -26,8 +26,11 @@ struct InvParams {
     size_t coef_stride;
     uint8_t *r, *g, *b;
     size_t plane_stride;      // bytes between images (= plane_bytes)
-    uint32_t W, H, HU, VU;
+    uint32_t W, H, HU, VU;    // HU x VU MCUs of (8*hmax) x (8*vmax) pixels
     int gray;
+    // general frame layout (k_inv_transform_f64): blocks per MCU, luma blocks per MCU, sampling factors
+    uint32_t nb, ny, ncomp, hmax, vmax;
+    uint32_t hs[3], vs[3];
     unsigned long long* guard_counter;
     uint16_t qt[3][64];       // per component, natural order
     float M[3][64];           // q * aan_v * aan_u / 8: dequantisation folded with the AAN input scaling
@@ -66,7 +69,11 @@ __device__ __forceinline__ uint8_t ref_G(int y, int cb, int cr)
 }
 __device__ __forceinline__ uint8_t ref_B(int y, int cb) { return revise(__dadd_rn(double(y), __dmul_rn(double(cb - 128), 1.7718))); }
 
-// ---- validation build: FP64 separable IDCT ----------------------------------------------------------
+// ---- general layouts + validation build: FP64 separable IDCT -----------------------------------------------
+// Handles every frame layout the device decoder accepts (1 or 3 components, luma H, V in {1, 2}, chroma 1x1): the
+// production kernel below is specialised for jpezy's own 2x2 / 1x1 / 1x1.  One CTA = kMcuPerCta MCUs of one MCU row.
+// Pixel replication of decode_mcu (src/decoder/jpezy_decoder.hpp:519-524): sample (py / dupy, px / dupx) of the
+// component's blocks, dup = max factor / component factor.
 __global__ void __launch_bounds__(kFwdThreads) k_inv_transform_f64(const InvParams p)
 {
     __shared__ int s_dq[kBlkPerCta][64];                 // dequantised, natural order
@@ -79,23 +86,25 @@ __global__ void __launch_bounds__(kFwdThreads) k_inv_transform_f64(const InvPara
     const uint32_t my = blockIdx.y;
     const size_t img = blockIdx.z;
     const uint32_t nvalid = min(uint32_t(kMcuPerCta), p.HU - mx0);
+    const uint32_t nb = p.nb, ny = p.ny, nblk = kMcuPerCta * nb;      // nb <= 6
 
-    const int16_t* src = p.coefs + img * p.coef_stride + (size_t(my) * p.HU + mx0) * 384;
-    for (uint32_t e = t; e < kBlkPerCta * 64; e += kFwdThreads) {
+    const int16_t* src = p.coefs + img * p.coef_stride + (size_t(my) * p.HU + mx0) * nb * 64;
+    for (uint32_t e = t; e < nblk * 64; e += kFwdThreads) {
         const uint32_t blk = e >> 6, n = e & 63;
-        const int comp = (blk % 6) < 4 ? 0 : int(blk % 6) - 3;
+        const uint32_t k = blk % nb;
+        const int comp = k < ny ? 0 : int(k - ny) + 1;
         const int nat = cC.zz[n];
-        const int c = (blk / 6) < nvalid ? int(src[e]) : 0;
+        const int c = (blk / nb) < nvalid ? int(src[e]) : 0;
         s_dq[blk][nat] = c * int(p.qt[comp][nat]);
     }
     __syncthreads();
-    if (t < kBlkPerCta) {
+    if (uint32_t(t) < nblk) {
         unsigned long long m = 0;
         for (int i = 0; i < 64; ++i)
             if (s_dq[t][i]) m |= 1ull << i;
         s_nz[t] = m;
     }
-    for (int task = t; task < kBlkPerCta * 8; task += kFwdThreads) {
+    for (uint32_t task = t; task < nblk * 8; task += kFwdThreads) {
         const int blk = task >> 3, u = task & 7;
         double col[8];
 #pragma unroll
@@ -110,7 +119,7 @@ __global__ void __launch_bounds__(kFwdThreads) k_inv_transform_f64(const InvPara
     }
     __syncthreads();
     unsigned long long guard_hits = 0;
-    for (int task = t; task < kBlkPerCta * 8; task += kFwdThreads) {
+    for (uint32_t task = t; task < nblk * 8; task += kFwdThreads) {
         const int blk = task >> 3, y = task & 7;
         double row[8];
 #pragma unroll
@@ -137,20 +146,28 @@ __global__ void __launch_bounds__(kFwdThreads) k_inv_transform_f64(const InvPara
     uint8_t* R = p.r + img * p.plane_stride;
     uint8_t* G = p.g + img * p.plane_stride;
     uint8_t* B = p.b + img * p.plane_stride;
-    for (int e = t; e < 16 * 128; e += kFwdThreads) {
-        const int ry = e >> 7, cx = e & 127;
-        const uint32_t gx = mx0 * 16u + cx;
-        if (gx >= p.W) continue;
-        const int mcu = cx >> 4;
-        const int k = (ry >> 3) * 2 + ((cx & 15) >> 3);
-        const int yv = s_pix[mcu * 6 + k][(ry & 7) * 8 + (cx & 7)];
-        const size_t idx = (size_t(my) * 16 + ry) * p.W + gx;
+    const uint32_t mw = 8 * p.hmax, mh = 8 * p.vmax;             // MCU size in pixels
+    const uint32_t dx1 = p.ncomp == 3 ? p.hmax / p.hs[1] : 1, dy1 = p.ncomp == 3 ? p.vmax / p.vs[1] : 1;
+    const uint32_t dx2 = p.ncomp == 3 ? p.hmax / p.hs[2] : 1, dy2 = p.ncomp == 3 ? p.vmax / p.vs[2] : 1;
+    const uint32_t dx0 = p.hmax / p.hs[0], dy0 = p.vmax / p.vs[0];
+    for (uint32_t e = t; e < mh * kMcuPerCta * mw; e += kFwdThreads) {
+        const uint32_t ry = e / (kMcuPerCta * mw), cx = e - ry * (kMcuPerCta * mw);
+        const uint32_t mcu = cx / mw, px = cx - mcu * mw;
+        const uint32_t gx = (mx0 + mcu) * mw + px;
+        if (mcu >= nvalid || gx >= p.W) continue;
+        const uint32_t sx0 = px / dx0, sy0 = ry / dy0;
+        const int yv = s_pix[mcu * nb + (sy0 >> 3) * p.hs[0] + (sx0 >> 3)][(sy0 & 7) * 8 + (sx0 & 7)];
+        const size_t idx = (size_t(my) * mh + ry) * p.W + gx;
         if (p.gray) {
             const uint8_t v = revise(double(yv));
             R[idx] = v, G[idx] = v, B[idx] = v;
         } else {
-            const int cpos = (ry >> 1) * 8 + ((cx & 15) >> 1);
-            const int cb = s_pix[mcu * 6 + 4][cpos], cr = s_pix[mcu * 6 + 5][cpos];
+            int cb = 128, cr = 128;      // comp tiles of absent components stay 0x80 (src/decoder/jpezy_decoder.hpp:105)
+            if (p.ncomp == 3) {
+                const uint32_t sx1 = px / dx1, sy1 = ry / dy1, sx2 = px / dx2, sy2 = ry / dy2;
+                cb = s_pix[mcu * nb + ny + (sy1 >> 3) * p.hs[1] + (sx1 >> 3)][(sy1 & 7) * 8 + (sx1 & 7)];
+                cr = s_pix[mcu * nb + ny + p.hs[1] * p.vs[1] + (sy2 >> 3) * p.hs[2] + (sx2 >> 3)][(sy2 & 7) * 8 + (sx2 & 7)];
+            }
             R[idx] = ref_R(yv, cr), G[idx] = ref_G(yv, cb, cr), B[idx] = ref_B(yv, cb);
         }
     }

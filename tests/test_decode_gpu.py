@@ -121,11 +121,12 @@ def test_unsupported_layouts_are_refused(ctx):
     with pytest.raises(J.JpezyError) as e:
         ctx.decode(b"\x00" * 64, f)
     assert e.value.code == capi.EUNSUPPORTED
-    f = J.default_frame(64, 64)
-    f.hs[0] = 1
-    with pytest.raises(J.JpezyError) as e:
-        ctx.decode(b"\x00" * 64, f)
-    assert e.value.code == capi.EUNSUPPORTED
+    for comp, h in ((1, 2), (0, 3)):          # sub-sampled luma relative to chroma / factors above 2: not on the device
+        f = J.default_frame(64, 64)
+        f.hs[comp] = h
+        with pytest.raises(J.JpezyError) as e:
+            ctx.decode(b"\x00" * 64, f)
+        assert e.value.code == capi.EUNSUPPORTED
 
 
 def test_custom_quant_and_huffman_tables_are_data(ctx, oracle):

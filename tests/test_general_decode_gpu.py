@@ -1,0 +1,78 @@
+"""-m gpu: baseline JPEGs that jpezy's own encoder never writes but its decoder accepts: other sampling
+factors, one component, quality-scaled quantisation tables, component ids 1..3 -- produced here with Pillow, decoded through
+the drop-in CLI (host marker parser of include/jpezy/jpezy_decoder.hpp + jpezyb200_decode) and compared with the oracle
+restatement of the reference decoder (which equals the reference's own decoder on these files, tests/test_oracle_vs_ref.py
+and the live check below).  Bar: identical samples."""
+import io
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as orc
+
+pytestmark = pytest.mark.gpu
+PIL = pytest.importorskip("PIL.Image")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEC = os.path.join(ROOT, "jpezy_b200", "bin", "jpezy_decode")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "jpezy_b200", "cli"), "-s"])
+
+
+def picture(W, H, seed):
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:H, 0:W]
+    img = np.stack([(x * 3 + y) % 256, (x + 2 * y) % 256, (x * y // 7) % 256], -1).astype(np.int64)
+    img = img // 2 + rng.integers(0, 128, (H, W, 3))
+    img[: H // 3, : W // 2] = [200, 30, 90]          # a flat patch: DC-only blocks, values on rounding boundaries
+    return img.clip(0, 255).astype(np.uint8)
+
+
+def jpeg_bytes(img, mode, **kw):
+    buf = io.BytesIO()
+    im = PIL.fromarray(img if mode == "RGB" else img[..., 0], mode)
+    im.save(buf, "JPEG", **kw)
+    return buf.getvalue()
+
+
+CASES = [("444", "RGB", dict(quality=75, subsampling=0)), ("422", "RGB", dict(quality=75, subsampling=1)),
+         ("420", "RGB", dict(quality=75, subsampling=2)), ("420_q95", "RGB", dict(quality=95, subsampling=2)),
+         ("444_q30", "RGB", dict(quality=30, subsampling=0)), ("gray", "L", dict(quality=80)),
+         ("gray_q100", "L", dict(quality=100)), ("422_optimized_tables", "RGB", dict(quality=60, subsampling=1, optimize=True))]
+
+
+@pytest.mark.parametrize("name,mode,kw", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("W,H", [(70, 45), (16, 16), (8, 8), (129, 257), (640, 360)])
+@pytest.mark.parametrize("gray_out", [False, True])
+def test_general_baseline_decode_matches_reference_decoder(tmp_path, oracle, name, mode, kw, W, H, gray_out):
+    if gray_out and (W, H) != (70, 45):
+        pytest.skip("--gray output checked on one size")
+    f = jpeg_bytes(picture(W, H, 7), mode, **kw)
+    jpg, out = tmp_path / "in.jpg", tmp_path / "out.ppm"
+    jpg.write_bytes(f)
+    Wd, Hd, R0, G0, B0 = oracle.decode(f, gray=gray_out)
+    p = subprocess.run([DEC, str(jpg), str(out)] + (["--gray"] if gray_out else []), capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    lines = out.read_text().split("\n")
+    assert lines[2] == "%d %d" % (W, H)
+    vals = np.array(" ".join(lines[4:]).split(), dtype=np.int64).reshape(-1, 3)
+    d = [np.abs(vals[:, k] - a[: W * H]) for k, a in enumerate((R0, G0, B0))]
+    assert max(int(x.max()) for x in d) <= 1, "more than 1 away from the reference decoder"
+    assert sum(int((x != 0).sum()) for x in d) == 0
+    if orc.ref_dir() is not None and (W, H) == (70, 45):        # the reference's own CLI writes the same PPM
+        ref = orc.Reference()
+        q = subprocess.run([ref.decode_exe, str(jpg), str(tmp_path / "ref.ppm")] + (["--gray"] if gray_out else []), capture_output=True, text=True)
+        assert q.returncode == 0 and (tmp_path / "ref.ppm").read_text() == out.read_text()
+
+
+def test_restart_intervals_are_refused_not_misdecoded(tmp_path):
+    f = jpeg_bytes(picture(64, 48, 3), "RGB", quality=75, subsampling=2, restart_marker_blocks=2)
+    jpg = tmp_path / "dri.jpg"
+    jpg.write_bytes(f)
+    p = subprocess.run([DEC, str(jpg), str(tmp_path / "o.ppm")], capture_output=True, text=True)
+    assert p.returncode == 1 and "decode failed" in p.stderr and "restart intervals" in p.stderr
