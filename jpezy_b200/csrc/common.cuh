@@ -76,7 +76,7 @@ struct jpezyb200_ctx {
 
     // scratch
     jz_devbuf coefs, blk_off, tile_sum, tile_base, img_bits, ustream, ff_sum, ff_base, planes_in, planes_out, scan_io, sizes_io;
-    jz_devbuf dec_scanbytes, dec_chunk_cnt, dec_chunk_base, dec_ubytes, dec_state, dec_dirty, dec_subblk, dec_dc, dec_status, dec_changed;
+    jz_devbuf dec_scanbytes, dec_chunk_cnt, dec_chunk_base, dec_ubytes, dec_state, dec_dirty, dec_subblk, dec_dc, dec_status, dec_changed, dec_mcnt, dec_mbase, dec_seg;
     jz_devbuf shard_geom;      // ShardGeom + scratch of the MCU-row sharded encoder (enc_shard.cuh)
     void* shard_state = nullptr;   // host copy of the launch parameters between the phases (capi_shard.inc)
     void* h_pinned = nullptr;

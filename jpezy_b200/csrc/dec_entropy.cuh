@@ -67,6 +67,13 @@ struct DecParams {
     uint32_t* chunk_cnt;      // [nimg][nchunk] kept bytes per chunk
     uint64_t* chunk_base;     // [nimg][nchunk]
     uint64_t* ubytes;         // [nimg] un-stuffed byte count
+    // restart intervals (DRI, src/decoder/jpezy_decoder.hpp:152-163,400-404): 0 = none
+    uint32_t dri;             // MCUs per restart interval
+    uint32_t nseg;            // restart segments per image = ceil(nmcu / dri)
+    uint32_t* chunk_mcnt;     // [nimg][nchunk] RSTn markers per chunk
+    uint64_t* chunk_mbase;    // [nimg][nchunk]
+    uint64_t* nmarkers;       // [nimg]
+    uint64_t* seg_start;      // [nimg][nseg + 1] first un-stuffed byte of every segment (segment 0: 0)
     // synchronisation
     uint32_t sub_bits;        // subsequence length in bits (128, 256 or 512)
     uint32_t nsub;            // subsequences per image (capacity)
@@ -214,18 +221,26 @@ __device__ __forceinline__ void load_span(const uint8_t* __restrict__ ustream, u
 
 // ---- D0: un-stuffing -------------------------------------------------------------------------------
 // keep[i] = !(byte[i] == 0x00 && byte[i-1] == 0xFF)
-__device__ __forceinline__ uint32_t keep_mask16(const uint8_t* __restrict__ src, uint64_t i0, uint64_t n, uint8_t* bytes)
+// dri: RSTn markers (FF D0..D7) are dropped as well; bit i of *markers = byte i is the FF of such a marker
+__device__ __forceinline__ uint32_t keep_mask16(const uint8_t* __restrict__ src, uint64_t i0, uint64_t n, uint8_t* bytes, bool dri, uint32_t* markers)
 {
-    uint32_t m = 0;
+    uint32_t m = 0, mk = 0;
     uint8_t prev = i0 ? src[i0 - 1] : 0;
+    uint8_t c = i0 < n ? src[i0] : 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const uint64_t idx = i0 + i;
-        const uint8_t c = idx < n ? src[idx] : 0;
+        const uint8_t nxt = idx + 1 < n ? src[idx + 1] : 0;
         bytes[i] = c;
-        if (idx < n && !(c == 0 && prev == 0xff)) m |= 1u << i;
+        const bool stuffed = c == 0 && prev == 0xff;
+        const bool rst_ff = dri && c == 0xff && (nxt & 0xf8) == 0xd0;
+        const bool rst_dx = dri && prev == 0xff && (c & 0xf8) == 0xd0;
+        if (idx < n && !stuffed && !rst_ff && !rst_dx) m |= 1u << i;
+        if (idx < n && rst_ff) mk |= 1u << i;
         prev = c;
+        c = nxt;
     }
+    *markers = mk;
     return m;
 }
 
@@ -262,10 +277,15 @@ __global__ void __launch_bounds__(kDecThreads) k_unstuff_count(const DecParams p
     for (uint32_t ch = blockIdx.x; ch < nch; ch += gridDim.x) {
         uint8_t bytes[16];
         const uint64_t i0 = (uint64_t(ch) * kDecThreads + threadIdx.x) * 16;
-        const uint32_t m = i0 < n ? keep_mask16(src, i0, n, bytes) : 0u;
+        uint32_t mk = 0;
+        const uint32_t m = i0 < n ? keep_mask16(src, i0, n, bytes, p.dri != 0, &mk) : 0u;
         uint32_t total;
         cta_scan_excl(__popc(m), s_warp, &total);
         if (threadIdx.x == 0) p.chunk_cnt[img * p.nchunk + ch] = total;
+        if (p.dri) {
+            cta_scan_excl(__popc(mk), s_warp, &total);
+            if (threadIdx.x == 0) p.chunk_mcnt[img * p.nchunk + ch] = total;
+        }
     }
 }
 
@@ -304,10 +324,20 @@ __global__ void __launch_bounds__(kDecThreads) k_unstuff_write(const DecParams p
     for (uint32_t ch = blockIdx.x; ch < nch; ch += gridDim.x) {
         uint8_t bytes[16];
         const uint64_t i0 = (uint64_t(ch) * kDecThreads + threadIdx.x) * 16;
-        const uint32_t m = i0 < n ? keep_mask16(src, i0, n, bytes) : 0u;
+        uint32_t mk = 0;
+        const uint32_t m = i0 < n ? keep_mask16(src, i0, n, bytes, p.dri != 0, &mk) : 0u;
         uint32_t total;
         const uint32_t off = cta_scan_excl(__popc(m), s_warp, &total);
         uint64_t o = p.chunk_base[img * p.nchunk + ch] + off;
+        if (p.dri) {
+            // the segment after the k-th marker starts at the next kept byte (marker bytes are not kept)
+            const uint32_t moff = cta_scan_excl(__popc(mk), s_warp, &total);
+            uint64_t k = p.chunk_mbase[img * p.nchunk + ch] + moff;
+            for (uint32_t mm = mk; mm; mm &= mm - 1, ++k) {
+                const int i = __ffs(int(mm)) - 1;
+                if (k + 1 <= p.nseg) p.seg_start[img * (p.nseg + 1) + k + 1] = o + __popc(m & ((1u << i) - 1u));
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i)
             if (m & (1u << i)) dst[o++] = bytes[i];
@@ -498,6 +528,75 @@ __global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p)
     br.init(s_span, pos);
     int corrupt = 0;
     decode_span<true>(br, b, z, n, start + p.sub_bits, limit, s_slow, s_fast, p.coefs + img * p.coef_stride, blk, p.nblk, &corrupt, p.nb, p.ny);
+    if (corrupt && p.status) p.status[img] = JPEZYB200_ECORRUPT;
+}
+
+// ---- restart intervals: every segment is self-contained (predictors reset, byte aligned), one thread each --------
+// restart_interval_check (src/decoder/jpezy_decoder.hpp:152-163): after `dri` MCUs the reference reads the next marker and
+// resets pred_dct[]; the segments between the markers were located by the un-stuffing pass (seg_start).
+__global__ void __launch_bounds__(128) k_decode_segments(const DecParams p)
+{
+    __shared__ __align__(16) uint32_t s_fast[4][1 << kLutBits];
+    __shared__ __align__(16) HuffSlow s_slow[4];
+    load_dec_tabs(p.tabs, s_fast, s_slow);
+    __syncthreads();
+    const size_t img = blockIdx.y;
+    const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= p.nseg) return;
+    const uint64_t nmark = p.nmarkers[img];
+    const uint64_t ubytes = p.ubytes[img];
+    if (nmark + 1 < p.nseg) {                       // fewer RSTn markers than the frame needs
+        if (seg == 0 && p.status) p.status[img] = JPEZYB200_ECORRUPT;
+        return;
+    }
+    const uint64_t b0 = seg == 0 ? 0 : p.seg_start[img * (p.nseg + 1) + seg];
+    const uint64_t b1 = seg + 1 < p.nseg ? p.seg_start[img * (p.nseg + 1) + seg + 1] : ubytes;
+    if (b0 > ubytes || b1 > ubytes || b1 < b0 || (b1 - b0) * 8 > 0xfffffff0ull) {
+        if (p.status) p.status[img] = JPEZYB200_ECORRUPT;
+        return;
+    }
+    // the bit reader works on 32-bit words: start at the word that holds byte b0
+    const uint8_t* base = p.ustream + img * p.uslot;
+    const uint64_t w0 = b0 & ~uint64_t(3);
+    BitBuf br;
+    br.init(reinterpret_cast<const uint32_t*>(base + w0), uint32_t(b0 - w0) * 8u);
+    const uint32_t limit = uint32_t((b1 - w0) * 8);
+    const uint32_t mcu0 = seg * p.dri, mcu1 = min(p.nmcu, mcu0 + p.dri);
+    int16_t* out = p.coefs + img * p.coef_stride;
+    int pred[3] = {0, 0, 0};
+    int corrupt = 0;
+    for (uint32_t m = mcu0; m < mcu1 && !corrupt; ++m) {
+        for (uint32_t k = 0; k < p.nb; ++k) {
+            const uint32_t comp = k < p.ny ? 0u : k - p.ny + 1u;
+            const uint32_t cls = comp ? 1u : 0u;
+            int16_t* blk = out + (size_t(m) * p.nb + k) * 64;
+            uint32_t z = 0;
+            while (z < 64u) {
+                if (br.pos >= limit) { corrupt = 1; break; }
+                br.refill();
+                const uint32_t w = br.peek32();
+                const uint32_t ti = (z == 0u ? 0u : 2u) + cls;
+                uint32_t e = s_fast[ti][w >> (32 - kLutBits)];
+                if (e == 0u) e = huff_lookup_slow(s_slow + ti, w);
+                if (e == 0u) { corrupt = 1; break; }
+                br.skip(int(e & 31u));
+                const uint32_t dz = (e >> 8) & 127u, len = (e >> 16) & 31u, sz = e >> 21;
+                const uint32_t kk = z + dz - 1u;
+                if (kk > 63u && dz != 64u) { corrupt = 1; break; }
+                if (sz) {
+                    const uint32_t vbits = (w << len) >> (32 - sz);
+                    int v = int(vbits);
+                    if (!(vbits & (1u << (sz - 1)))) v -= (1 << sz) - 1;
+                    if (z == 0u) v = (pred[comp] += v);
+                    blk[kk] = int16_t(v);
+                } else if (z == 0u) {
+                    blk[0] = int16_t(pred[comp]);
+                }
+                z += dz;
+            }
+            if (corrupt) break;
+        }
+    }
     if (corrupt && p.status) p.status[img] = JPEZYB200_ECORRUPT;
 }
 

@@ -116,11 +116,6 @@ def test_truncated_stream_is_reported_corrupt(ctx, oracle):
 
 
 def test_unsupported_layouts_are_refused(ctx):
-    f = J.default_frame(64, 64)
-    f.restart_interval = 4
-    with pytest.raises(J.JpezyError) as e:
-        ctx.decode(b"\x00" * 64, f)
-    assert e.value.code == capi.EUNSUPPORTED
     for comp, h in ((1, 2), (0, 3)):          # sub-sampled luma relative to chroma / factors above 2: not on the device
         f = J.default_frame(64, 64)
         f.hs[comp] = h

@@ -70,9 +70,31 @@ def test_general_baseline_decode_matches_reference_decoder(tmp_path, oracle, nam
         assert q.returncode == 0 and (tmp_path / "ref.ppm").read_text() == out.read_text()
 
 
-def test_restart_intervals_are_refused_not_misdecoded(tmp_path):
+DRI_CASES = [("420_dri2", "RGB", dict(quality=75, subsampling=2, restart_marker_blocks=2)),
+             ("444_dri_row", "RGB", dict(quality=80, subsampling=0, restart_marker_rows=1)),
+             ("422_dri7", "RGB", dict(quality=50, subsampling=1, restart_marker_blocks=7)),
+             ("gray_dri5", "L", dict(quality=90, restart_marker_blocks=5)),
+             ("420_dri_larger_than_image", "RGB", dict(quality=75, subsampling=2, restart_marker_blocks=60000))]
+
+
+@pytest.mark.parametrize("name,mode,kw", DRI_CASES, ids=[c[0] for c in DRI_CASES])
+@pytest.mark.parametrize("W,H", [(70, 45), (16, 16), (333, 200)])
+def test_restart_intervals(tmp_path, oracle, name, mode, kw, W, H):
+    """DRI files (src/decoder/jpezy_decoder.hpp:152-163,400-404): segments located while un-stuffing, one thread per segment"""
+    f = jpeg_bytes(picture(W, H, 11), mode, **kw)
+    assert (b"\xff\xdd" in f) == ("larger" not in name or True)
+    jpg, out = tmp_path / "in.jpg", tmp_path / "out.ppm"
+    jpg.write_bytes(f)
+    _, _, R0, G0, B0 = oracle.decode(f)
+    p = subprocess.run([DEC, str(jpg), str(out)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    vals = np.array(" ".join(out.read_text().split("\n")[4:]).split(), dtype=np.int64).reshape(-1, 3)
+    assert all((vals[:, k] == a[: W * H]).all() for k, a in enumerate((R0, G0, B0)))
+
+
+def test_truncated_restart_stream_fails_cleanly(tmp_path):
     f = jpeg_bytes(picture(64, 48, 3), "RGB", quality=75, subsampling=2, restart_marker_blocks=2)
     jpg = tmp_path / "dri.jpg"
-    jpg.write_bytes(f)
+    jpg.write_bytes(f[: len(f) * 2 // 3])
     p = subprocess.run([DEC, str(jpg), str(tmp_path / "o.ppm")], capture_output=True, text=True)
-    assert p.returncode == 1 and "decode failed" in p.stderr and "restart intervals" in p.stderr
+    assert p.returncode == 1 and "decode failed" in p.stderr
