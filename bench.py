@@ -238,6 +238,88 @@ def run_sharded(args, wl):
     ctx.close()
 
 
+def run_sharded_gray(args, wl):
+    """C4 on N GPUs, --shard: ONE 8192x8192 --gray image, encode sharded by MCU rows (collectives + P2P stitch) then decode with
+    the entropy stage replicated on every rank and the transform stage sharded by MCU rows (P2P stores into rank 0's planes)."""
+    import torch
+    import torch.distributed as dist
+    import jpezy_b200 as J
+    from jpezy_b200 import capi, shard
+    args.steps = args.steps or 20
+    args.warmup = max(args.warmup if args.warmup is not None else 3, 3)
+    rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = J.Context(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sp = stream.cuda_stream
+    W, H, gray = args.width or wl["W"], args.height or wl["H"], True
+    row0, nrows = shard.partition_mcu_rows((H + 15) // 16, world)[rank]
+    y0, ny = shard.pixel_rows(H, row0, nrows)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    planes = torch.empty((3, ny, W), dtype=torch.uint8, device="cuda")
+    ctx.synth_rows_dev(planes[0], planes[1], planes[2], W, y0, ny, frame=0, family=args.family, stream=sp)
+    grp = shard.DistGroup(dist, torch.device("cuda", local_rank))
+    cap = max(W * H // 2, 1 << 20)
+    enc = shard.ShardedEncoder(ctx, grp, cap)
+    frame = J.default_frame(W, H)
+    dec = shard.ShardedDecoder(ctx, grp, frame, cap)
+    enc.encode(planes[0], planes[1], planes[2], W, H, row0, nrows, y0, gray, stream=sp)
+    seg, _ = enc.result()
+    nbytes = torch.zeros(1, dtype=torch.int64, device="cuda")
+    if rank == 0:
+        nbytes[0] = len(seg)
+        dec.scan[: len(seg)] = torch.frombuffer(bytearray(seg), dtype=torch.uint8).cuda()
+    dist.broadcast(nbytes, src=0)
+    n_scan = int(nbytes.item())
+
+    def step():
+        enc.encode(planes[0], planes[1], planes[2], W, H, row0, nrows, y0, gray, stream=sp)
+        dec.decode(n_scan, gray, stream=sp)        # (the stream of the previous encode: same bytes every step)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler.mark = True
+    l0 = ctx.stat(capi.STAT_KERNEL_LAUNCHES)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.stat(capi.STAT_KERNEL_LAUNCHES) - l0
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    sampler.mark = None
+    out = dec.result()
+    sampler.stop_flag = True
+    if rank == 0:
+        ok = bool(out is not None and out[0][: W * 16].any())
+        line = {"metric": "encode+decode MPix/s", "value": float(W) * H * args.steps / (ms * 1e-3) / 1e6, "unit": "MPix/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+                "config": {"workload": wl["name"] + " (one image sharded by MCU rows)", "width": W, "height": H, "gray": True,
+                           "family": "S-photo" if args.family == 0 else "S-noise", "l2": "inputs larger than L2",
+                           "sharding": "encode: MCU rows + 3 all-gathers + P2P stitch; decode: segment broadcast, entropy stage replicated, "
+                                       "transform stage by MCU rows with P2P stores into rank 0"},
+                "clocks": sampler.summary(), "gpu_launches": int(launches), "e2e": None, "roofline": None, "cpu_baseline": None,
+                "stages": {"stream_bytes": n_scan, "decoded_ok": ok}}
+        print(json.dumps(line))
+    dec.close()
+    enc.close()
+    dist.destroy_process_group()
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -250,6 +332,7 @@ def main():
     ap.add_argument("--ring", type=int, default=None, help="distinct input/output frame sets rotated between steps")
     ap.add_argument("--width", type=int, default=None, help="c5: override the image width")
     ap.add_argument("--height", type=int, default=None, help="c5: override the image height")
+    ap.add_argument("--shard", action="store_true", help="c4 under torchrun: ONE image split by MCU rows over the ranks (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -262,6 +345,8 @@ def main():
         return run_reference(args, wl)
     if args.workload == "c5":
         return run_sharded(args, wl)
+    if args.workload == "c4" and int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.shard:
+        return run_sharded_gray(args, wl)
     args.steps = args.steps or 200
     args.warmup = args.warmup if args.warmup is not None else 10
     args.warmup = max(args.warmup, 3)
@@ -455,7 +540,7 @@ def main():
     if rank == 0:
         line = {"metric": "encode+decode MPix/s", "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
                 "config": {"workload": wl["name"], "width": W, "height": H, "batch_per_gpu": B, "gray": gray,
                            "family": "S-photo" if args.family == 0 else "S-noise",
                            "l2": "ring of %d distinct input/output frame sets (%.0f MB) rotated between steps; > 126 MB L2" % (

@@ -201,6 +201,16 @@ JPEZYB200_API int jpezyb200_shard_encode_c(jpezyb200_ctx* ctx, const uint64_t* d
 JPEZYB200_API int jpezyb200_shard_encode_d(jpezyb200_ctx* ctx, const uint64_t* d_all_bytes, uint8_t* d_dst, size_t dst_cap,
                              uint64_t* d_total_bytes, int32_t* d_overflow, void* stream);
 
+/* One image decoded by several GPUs.  The restart-less entropy-coded segment is decoded whole on every rank (replicas:
+ * its self-synchronising decoder is latency bound and a byte-range split would have to redistribute the coefficients by MCU
+ * row afterwards, SURVEY.md 8e "fall back to replicas for the entropy stage"); dequantisation, IDCT, upsampling and colour
+ * conversion (src/decoder/jpezy_decoder.hpp:645-676, 531-578) are sharded by MCU rows: this rank produces pixel rows of MCU
+ * rows [mcu_row0, mcu_row0 + mcu_rows) and stores them straight into the full planes d_r/d_g/d_b, which may be mapped from
+ * another GPU (jpezyb200_ipc_*).  The rank that owns the last MCU row also clears the planes' tail. */
+JPEZYB200_API int jpezyb200_shard_decode_dev(jpezyb200_ctx* ctx, const uint8_t* d_scan, size_t scan_bytes, const jpezyb200_frame* f,
+                               int gray, uint32_t mcu_row0, uint32_t mcu_rows, uint8_t* d_r, uint8_t* d_g, uint8_t* d_b,
+                               size_t plane_bytes, int32_t* d_status, void* stream);
+
 /* Peer-visible device buffer for the stitched stream: the owning rank allocates and exports a 64-byte CUDA IPC
  * handle, the other ranks (other processes, other GPUs of the box) map it and pass the mapped pointer as d_dst. */
 JPEZYB200_API int jpezyb200_ipc_alloc(jpezyb200_ctx* ctx, size_t bytes, void** d_ptr, uint8_t handle[64]);

@@ -17,7 +17,7 @@ EXPORTS = [
     "jpezyb200_decode", "jpezyb200_decode_batch_dev", "jpezyb200_entropy_decode_dev", "jpezyb200_transform_inv_dev",
     "jpezyb200_synth_dev", "jpezyb200_synth_rows_dev", "jpezyb200_shard_encode_a", "jpezyb200_shard_encode_b",
     "jpezyb200_shard_encode_c", "jpezyb200_shard_encode_d", "jpezyb200_ipc_alloc", "jpezyb200_ipc_open", "jpezyb200_ipc_close",
-    "jpezyb200_ipc_free",
+    "jpezyb200_ipc_free", "jpezyb200_shard_decode_dev",
 ]
 
 
@@ -88,6 +88,7 @@ def load_library():
     L.jpezyb200_shard_encode_b.argtypes = [vp, vp, vp, vp]
     L.jpezyb200_shard_encode_c.argtypes = [vp, vp, u32, u32, vp, vp]
     L.jpezyb200_shard_encode_d.argtypes = [vp, vp, u8p, sz, vp, vp, vp]
+    L.jpezyb200_shard_decode_dev.argtypes = [vp, u8p, sz, C.POINTER(Frame), C.c_int, u32, u32, u8p, u8p, u8p, sz, vp, vp]
     L.jpezyb200_ipc_alloc.argtypes = [vp, sz, C.POINTER(vp), C.c_char_p]
     L.jpezyb200_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.jpezyb200_ipc_close.argtypes = [vp, vp]
@@ -251,3 +252,7 @@ class Context:
 
     def ipc_free(self, ptr):
         self._chk(self.lib.jpezyb200_ipc_free(self.h, ptr))
+
+    def shard_decode_dev(self, d_scan, scan_bytes, frame, gray, mcu_row0, mcu_rows, d_r, d_g, d_b, plane_len, d_status=None, stream=None):
+        self._chk(self.lib.jpezyb200_shard_decode_dev(self.h, _dp(d_scan), int(scan_bytes), C.byref(frame), int(gray), mcu_row0, mcu_rows,
+                                                      _dp(d_r), _dp(d_g), _dp(d_b), plane_len, _dp(d_status), stream))

@@ -29,6 +29,7 @@ struct InvParams {
     uint32_t W, H, HU, VU;    // HU x VU MCUs of (8*hmax) x (8*vmax) pixels
     int gray;
     // general frame layout (k_inv_transform_f64): blocks per MCU, luma blocks per MCU, sampling factors
+    uint32_t row0;            // first MCU row of this launch (MCU-row shards of one image)
     uint32_t nb, ny, ncomp, hmax, vmax;
     uint32_t hs[3], vs[3];
     unsigned long long* guard_counter;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(kFwdThreads) k_inv_transform_f64(const InvPara
 
     const int t = threadIdx.x;
     const uint32_t mx0 = blockIdx.x * kMcuPerCta;
-    const uint32_t my = blockIdx.y;
+    const uint32_t my = blockIdx.y + p.row0;
     const size_t img = blockIdx.z;
     const uint32_t nvalid = min(uint32_t(kMcuPerCta), p.HU - mx0);
     const uint32_t nb = p.nb, ny = p.ny, nblk = kMcuPerCta * nb;      // nb <= 6
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(kInvThreads, 3) k_inv_transform(const __grid_c
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t mx0 = blockIdx.x * kTileMcu;
-    const uint32_t my = blockIdx.y;
+    const uint32_t my = blockIdx.y + p.row0;
     const size_t img = blockIdx.z;
     const uint32_t nvalid = min(uint32_t(kTileMcu), p.HU - mx0);
     if (t == 0) *s_nfix = 0;

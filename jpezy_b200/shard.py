@@ -199,3 +199,95 @@ def encode_sharded_local(ctxs, planes, W, H, gray=False, dst_cap=None, device="c
     if int(ovf.sum().item()):
         raise RuntimeError("stitched stream does not fit dst_cap=%d" % dst_cap)
     return dst[: int(total.item())].cpu().numpy().tobytes(), [int(x) for x in info[:, 0].cpu().tolist()]
+
+
+class ShardedDecoder:
+    """One image decoded by all ranks of `group` (jpezyb200_shard_decode_dev).  The entropy-coded segment is broadcast
+    from rank 0 (the one real exchange: S bytes over NVLink) and decoded whole by every rank (replicas, see
+    include/jpezy_b200.h); the transform stage is sharded by MCU rows and every rank stores its pixel rows straight into
+    rank 0's planes, mapped through CUDA IPC."""
+
+    def __init__(self, ctx, group, frame, scan_cap):
+        import torch
+        from . import capi
+        self.torch, self.ctx, self.group, self.frame = torch, ctx, group, frame
+        self.plane_len = capi.plane_bytes(frame)
+        dev = group.device
+        self.scan = torch.zeros(int(scan_cap), dtype=torch.uint8, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        hs, vs = max(frame.hs[:frame.ncomp]), max(frame.vs[:frame.ncomp])
+        vu = -(-((frame.height + 7) // 8) // vs)
+        self.row0, self.nrows = partition_mcu_rows(vu, group.size)[group.rank]
+        self._owned = self._mapped = None
+        nbytes = 3 * self.plane_len
+        if group.size == 1:
+            self.planes_tensor = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            self.base = self.planes_tensor.data_ptr()
+        elif group.rank == 0:
+            self._owned, handle = ctx.ipc_alloc(nbytes)
+            self.base = self._owned
+            group.broadcast_object(handle, src=0)
+        else:
+            handle = group.broadcast_object(None, src=0)
+            self._mapped = ctx.ipc_open(handle)
+            self.base = self._mapped
+
+    def decode(self, scan_bytes, gray=False, stream=None):
+        """rank 0 holds the segment in self.scan[:scan_bytes]; all ranks call this together"""
+        if not stream:
+            raise ValueError("ShardedDecoder.decode needs torch's current non-default stream (torch.cuda.Stream)")
+        g = self.group
+        if g.size > 1:
+            g.dist.broadcast(self.scan[:scan_bytes], src=0)
+        pl = self.plane_len
+        self.ctx.shard_decode_dev(self.scan, scan_bytes, self.frame, gray, self.row0, self.nrows, self.base, self.base + pl,
+                                  self.base + 2 * pl, pl, self.status, stream=stream)
+
+    def result(self):
+        """rank 0, after a barrier: the three planes as numpy arrays (reference layout: stride W, padded length)"""
+        self.torch.cuda.synchronize()
+        self.group.barrier()
+        self.torch.cuda.synchronize()
+        if int(self.status.item()):
+            raise RuntimeError("entropy-coded segment could not be decoded (status %d)" % int(self.status.item()))
+        if self.group.rank != 0:
+            return None
+        n = 3 * self.plane_len
+        if self.group.size == 1:
+            flat = self.planes_tensor.cpu().numpy()
+        else:
+            class _Arr:
+                __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (int(self.base), False), "version": 2}
+            flat = self.torch.as_tensor(_Arr(), device=self.group.device).cpu().numpy()
+        pl = self.plane_len
+        return flat[:pl].copy(), flat[pl: 2 * pl].copy(), flat[2 * pl:].copy()
+
+    def close(self):
+        if self._mapped:
+            self.ctx.ipc_close(self._mapped)
+            self._mapped = None
+        self.group.barrier()
+        if self._owned:
+            self.ctx.ipc_free(self._owned)
+            self._owned = None
+
+
+def decode_sharded_local(ctxs, scan, frame, gray=False, device="cuda"):
+    """N ranks emulated on one device: every context decodes the segment and writes its MCU rows into the same planes."""
+    import torch
+    from . import capi
+    n = len(ctxs)
+    pl = capi.plane_bytes(frame)
+    hs, vs = max(frame.hs[:frame.ncomp]), max(frame.vs[:frame.ncomp])
+    vu = -(-((frame.height + 7) // 8) // vs)
+    planes = torch.full((3, pl), 0xAA, dtype=torch.uint8, device=device)       # poisoned: every byte must be written or cleared
+    d_scan = torch.from_numpy(np.frombuffer(scan, dtype=np.uint8).copy()).to(device)
+    st = torch.cuda.current_stream().cuda_stream
+    status = torch.zeros(n, dtype=torch.int32, device=device)
+    for k, (row0, nrows) in enumerate(partition_mcu_rows(vu, n)):
+        ctxs[k].shard_decode_dev(d_scan, len(scan), frame, gray, row0, nrows, planes[0], planes[1], planes[2], pl, status[k: k + 1], stream=st)
+    torch.cuda.synchronize()
+    if int(status.abs().sum().item()):
+        raise RuntimeError("decode failed")
+    h = planes.cpu().numpy()
+    return h[0], h[1], h[2]

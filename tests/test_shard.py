@@ -162,3 +162,21 @@ def test_sharded_encode_pad_zero_and_overflow(ctx, oracle):
     finally:
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,family,nranks,gray", [(64, 48, 0, 2, False), (200, 120, 1, 3, False), (333, 77, 0, 2, True),
+                                                   (640, 360, 1, 8, False), (40, 25, 2, 2, False), (1024, 1024, 0, 8, True)])
+def test_sharded_decode_matches_single_gpu(ctx, oracle, W, H, family, nranks, gray):
+    """transform stage sharded by MCU rows (entropy stage replicated): same planes as the whole-image decode, tail cleared"""
+    r, g, b = J.synth.image(family, W, H)
+    scan, _ = ctx.encode(r, g, b, W, H, gray=gray)
+    frame = J.default_frame(W, H)
+    want = ctx.decode(scan, frame, gray=gray)
+    ctxs = [J.Context(0) for _ in range(nranks)]
+    try:
+        got = shard.decode_sharded_local(ctxs, scan, frame, gray=gray)
+    finally:
+        for c in ctxs:
+            c.close()
+    assert all((a == b_).all() for a, b_ in zip(got, want))
