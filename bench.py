@@ -474,32 +474,59 @@ def main():
     stages = {"fwd_transform_ms": t_fwd, "entropy_encode_ms": t_ent, "entropy_decode_ms": t_dent, "inv_transform_ms": t_inv,
               "fwd_transform_GBs": bpp * B * npx / t_fwd / 1e6, "inv_transform_GBs": bpp * B * npx / t_inv / 1e6,
               "entropy_encode_Gbit_s": scan_bytes * 8 / t_ent / 1e6, "entropy_decode_Gbit_s": scan_bytes * 8 / t_dent / 1e6,
+              # scan efficiency = algorithmic bytes / bytes the kernels move (model of the passes listed in DESIGN.md 4.2):
+              #   encode: algorithmic 3 B/px coefficients read + S written; moved: coefficients read twice (lengths, scatter),
+              #           4 B/block of offsets written and read, un-stuffed stream zeroed + written + read twice, S written
+              #   decode: algorithmic S read + 3 B/px written; moved: S read twice + written once (un-stuffing), the spans read by
+              #           launch 0, launch 1 and the writing pass, 3 B/px zeroed, ~1 sector per non-zero coefficient group
+              #           (taken as 3 B/px), DC fix-up 2 x 32 B per block
+              "entropy_encode_scan_efficiency": (3.0 * B * npx + scan_bytes) / (6.0 * B * npx + 8.0 * B * npx / 64 * 1.5 + 5.0 * scan_bytes),
+              "entropy_decode_scan_efficiency": (3.0 * B * npx + scan_bytes) / (6.0 * scan_bytes + 6.0 * B * npx + 64.0 * B * npx * 1.5 / 64),
               "scan_bytes_per_step": scan_bytes, "bits_per_pixel": scan_bytes * 8 / (B * npx),
               "encode_MPix_s": B * npx / (t_fwd + t_ent) / 1e3, "decode_MPix_s": B * npx / (t_dent + t_inv) / 1e3}
 
     # ---- e2e: host buffers through jpezyb200_encode / jpezyb200_decode, pinned memory, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        nh = max(2, min(ring, 4))
-        hin = [[torch.empty(npx, dtype=torch.uint8).pin_memory() for _ in range(3)] for _ in range(nh)]
-        for k in range(nh):
-            for c in range(3):
-                hin[k][c].copy_(d_in[k % ring, c, 0].reshape(-1).cpu())
-        hscan = torch.empty(max(npx * 3, 10240), dtype=torch.uint8).pin_memory()
-        hout = [torch.empty(plane_len, dtype=torch.uint8).pin_memory() for _ in range(3)]
-        L = ctx.lib
         import ctypes as C
-        nbytes_c, nbits_c = C.c_size_t(0), C.c_uint64(0)
+        L = ctx.lib
+        if B == 1:
+            # one image per step: the per-image host entry points, as the reference's encoder / decoder objects are used
+            nh = max(2, min(ring, 4))
+            hin = [[torch.empty(npx, dtype=torch.uint8).pin_memory() for _ in range(3)] for _ in range(nh)]
+            for k in range(nh):
+                for c in range(3):
+                    hin[k][c].copy_(d_in[k % ring, c, 0].reshape(-1).cpu())
+            hscan = torch.empty(max(npx * 3, 10240), dtype=torch.uint8).pin_memory()
+            hout = [torch.empty(plane_len, dtype=torch.uint8).pin_memory() for _ in range(3)]
+            nbytes_c, nbits_c = C.c_size_t(0), C.c_uint64(0)
+            api = "jpezyb200_encode + jpezyb200_decode (host pointers, pinned)"
 
-        def e2e_step(k):
-            tot = 0
-            for _ in range(B):     # the host API is per image, as the reference's encoder/decoder objects are
+            def e2e_step(k):
                 ctx._chk(L.jpezyb200_encode(ctx.h, hin[k][0].data_ptr(), hin[k][1].data_ptr(), hin[k][2].data_ptr(), W, H, int(gray),
                                             hscan.data_ptr(), hscan.numel(), C.byref(nbytes_c), C.byref(nbits_c)))
                 ctx._chk(L.jpezyb200_decode(ctx.h, hscan.data_ptr(), nbytes_c.value, C.byref(frame), int(gray), hout[0].data_ptr(),
                                             hout[1].data_ptr(), hout[2].data_ptr(), plane_len))
-                tot += nbytes_c.value
-            return tot
+                return nbytes_c.value
+        else:
+            # a batch per step: the pipelined host batch entry points (copies of one group overlap the kernels of the previous one)
+            nh = 2
+            hin = [[torch.empty((B, npx), dtype=torch.uint8).pin_memory() for _ in range(3)] for _ in range(nh)]
+            for k in range(nh):
+                for c in range(3):
+                    hin[k][c].copy_(d_in[k % ring, c].reshape(B, npx).cpu())
+            hslot = max(npx // 2, 65536)
+            hscan = torch.empty((B, hslot), dtype=torch.uint8).pin_memory()
+            hout = [torch.empty((B, plane_len), dtype=torch.uint8).pin_memory() for _ in range(3)]
+            hnb = np.zeros(B, dtype=np.uint64)
+            hst = np.zeros(B, dtype=np.int32)
+            api = "jpezyb200_encode_batch + jpezyb200_decode_batch (host pointers, pinned, 3-stream pipeline)"
+
+            def e2e_step(k):
+                ctx.encode_batch(hin[k][0], hin[k][1], hin[k][2], W, H, B, gray, hscan, hslot, hnb)
+                ctx.decode_batch(hscan, hslot, hnb, B, frame, gray, hout[0], hout[1], hout[2], plane_len, hst)
+                assert not hst.any()
+                return int(hnb.sum())
         for i in range(3):
             e2e_step(i % nh)
         n_e2e = max(3, min(args.steps, 20))
@@ -516,8 +543,7 @@ def main():
             dt = float(t.item())
         sb /= n_e2e
         e2e = {"value": world * B * npx * n_e2e / dt / 1e6, "unit": "MPix/s", "h2d_bytes_per_step": int(3 * npx * B + sb),
-               "d2h_bytes_per_step": int(sb + 3 * plane_len * B), "steps": n_e2e,
-               "api": "jpezyb200_encode + jpezyb200_decode (host pointers, pinned)"}
+               "d2h_bytes_per_step": int(sb + 3 * plane_len * B), "steps": n_e2e, "api": api}
 
     sampler.stop_flag = True
     clocks = sampler.summary()

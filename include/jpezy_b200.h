@@ -64,6 +64,8 @@ enum {
     JPEZYB200_OPT_TRANSFORM = 2,  /* forward/inverse transform kernel variant: 0 = fast path with
                                      guard band + exact recompute (default), 1 = FP64 separable
                                      (validation build)                                           */
+    JPEZYB200_OPT_BATCH_GROUP_BYTES = 4, /* jpezyb200_encode_batch / decode_batch: host<->device bytes per pipeline stage
+                                     (default 96 MiB; images per group = value / (3 * pixels), at least 1)      */
     JPEZYB200_OPT_SYNC_ROUNDS = 3 /* self-synchronisation launches enqueued after the first one by the
                                      decoder: n > 0 = exactly n, no host round trip (default 3; one is
                                      needed on ordinary streams thanks to the warm-up overlap, later ones return at once); 0 = the
@@ -103,6 +105,14 @@ JPEZYB200_API int jpezyb200_encode(jpezyb200_ctx* ctx, const uint8_t* r, const u
 JPEZYB200_API int jpezyb200_encode_batch_dev(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g, const uint8_t* d_b, uint32_t W,
                                uint32_t H, uint32_t nimg, int gray, uint8_t* d_scan, size_t slot_bytes,
                                uint64_t* d_scan_bytes, uint64_t* d_scan_bits, void* stream);
+
+/* Batch of nimg images in HOST memory (image i: planes at r + i*W*H, segment at scan_out + i*slot_bytes, scan_bytes[i] = its
+ * length, UINT64_MAX when it did not fit).  Pipelined over three streams: the host->device copies of one group of images,
+ * the kernels of the previous group and the device->host copies of the one before overlap (pin the host buffers for the
+ * copies to be asynchronous).  The reference has no batch entry point: this is its encoder::encode() called nimg times
+ * (src/encoder/encode_io.hpp:163-165) with the PCIe transfers hidden.  Synchronises before returning. */
+JPEZYB200_API int jpezyb200_encode_batch(jpezyb200_ctx* ctx, const uint8_t* r, const uint8_t* g, const uint8_t* b, uint32_t W, uint32_t H,
+                           uint32_t nimg, int gray, uint8_t* scan_out, size_t slot_bytes, uint64_t* scan_bytes);
 
 /* Stage E1+E2 only: planar RGB -> quantised coefficients, int16, zig-zag order
  * (src/jpezy.hpp:36-45), block order Y0 Y1 Y2 Y3 Cb Cr per MCU, MCUs row-major
@@ -160,6 +170,11 @@ JPEZYB200_API int jpezyb200_decode(jpezyb200_ctx* ctx, const uint8_t* scan, size
 JPEZYB200_API int jpezyb200_decode_batch_dev(jpezyb200_ctx* ctx, const uint8_t* d_scan, size_t slot_bytes, const uint64_t* h_scan_bytes,
                                uint32_t nimg, const jpezyb200_frame* f, int gray, uint8_t* d_r, uint8_t* d_g, uint8_t* d_b,
                                size_t plane_bytes, int32_t* d_status, void* stream);
+
+/* Batch in HOST memory, pipelined like jpezyb200_encode_batch: segment i at scan + i*slot_bytes (scan_bytes[i] bytes), planes of
+ * image i at r + i*plane_bytes.  status (host, may be NULL) receives 0 or JPEZYB200_ECORRUPT per image. */
+JPEZYB200_API int jpezyb200_decode_batch(jpezyb200_ctx* ctx, const uint8_t* scan, size_t slot_bytes, const uint64_t* scan_bytes, uint32_t nimg,
+                           const jpezyb200_frame* f, int gray, uint8_t* r, uint8_t* g, uint8_t* b, size_t plane_bytes, int32_t* status);
 
 /* Stage D1 only: segment(s) -> coefficients (layout of jpezyb200_transform_fwd_dev, DC absolute). */
 JPEZYB200_API int jpezyb200_entropy_decode_dev(jpezyb200_ctx* ctx, const uint8_t* d_scan, size_t slot_bytes,

@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 OK, EINVAL, ECAPACITY, ECUDA, ENCCL, ECORRUPT, ENODEVICE, ENOMEM, EUNSUPPORTED, EAGAIN = range(10)
-OPT_PAD_ONES, OPT_TRANSFORM, OPT_SYNC_ROUNDS = 1, 2, 3
+OPT_PAD_ONES, OPT_TRANSFORM, OPT_SYNC_ROUNDS, OPT_BATCH_GROUP_BYTES = 1, 2, 3, 4
 STAT_KERNEL_LAUNCHES, STAT_GUARD_FWD, STAT_GUARD_INV, STAT_SYNC_ROUNDS, STAT_SYNC_ITERS0, STAT_SYNC_ITERS1 = 1, 2, 3, 4, 5, 6
 
 EXPORTS = [
@@ -17,7 +17,7 @@ EXPORTS = [
     "jpezyb200_decode", "jpezyb200_decode_batch_dev", "jpezyb200_entropy_decode_dev", "jpezyb200_transform_inv_dev",
     "jpezyb200_synth_dev", "jpezyb200_synth_rows_dev", "jpezyb200_shard_encode_a", "jpezyb200_shard_encode_b",
     "jpezyb200_shard_encode_c", "jpezyb200_shard_encode_d", "jpezyb200_ipc_alloc", "jpezyb200_ipc_open", "jpezyb200_ipc_close",
-    "jpezyb200_ipc_free", "jpezyb200_shard_decode_dev",
+    "jpezyb200_ipc_free", "jpezyb200_shard_decode_dev", "jpezyb200_encode_batch", "jpezyb200_decode_batch",
 ]
 
 
@@ -89,6 +89,8 @@ def load_library():
     L.jpezyb200_shard_encode_c.argtypes = [vp, vp, u32, u32, vp, vp]
     L.jpezyb200_shard_encode_d.argtypes = [vp, vp, u8p, sz, vp, vp, vp]
     L.jpezyb200_shard_decode_dev.argtypes = [vp, u8p, sz, C.POINTER(Frame), C.c_int, u32, u32, u8p, u8p, u8p, sz, vp, vp]
+    L.jpezyb200_encode_batch.argtypes = [vp, u8p, u8p, u8p, u32, u32, u32, C.c_int, u8p, sz, u64p]
+    L.jpezyb200_decode_batch.argtypes = [vp, u8p, sz, u64p, u32, C.POINTER(Frame), C.c_int, u8p, u8p, u8p, sz, vp]
     L.jpezyb200_ipc_alloc.argtypes = [vp, sz, C.POINTER(vp), C.c_char_p]
     L.jpezyb200_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.jpezyb200_ipc_close.argtypes = [vp, vp]
@@ -256,3 +258,11 @@ class Context:
     def shard_decode_dev(self, d_scan, scan_bytes, frame, gray, mcu_row0, mcu_rows, d_r, d_g, d_b, plane_len, d_status=None, stream=None):
         self._chk(self.lib.jpezyb200_shard_decode_dev(self.h, _dp(d_scan), int(scan_bytes), C.byref(frame), int(gray), mcu_row0, mcu_rows,
                                                       _dp(d_r), _dp(d_g), _dp(d_b), plane_len, _dp(d_status), stream))
+
+    # ---- pipelined host batches (numpy arrays or pinned torch tensors) ----
+    def encode_batch(self, r, g, b, W, H, nimg, gray, scan_out, slot_bytes, scan_bytes):
+        self._chk(self.lib.jpezyb200_encode_batch(self.h, _dp(r), _dp(g), _dp(b), W, H, nimg, int(gray), _dp(scan_out), slot_bytes, _dp(scan_bytes)))
+
+    def decode_batch(self, scan, slot_bytes, scan_bytes, nimg, frame, gray, r, g, b, plane_len, status=None):
+        self._chk(self.lib.jpezyb200_decode_batch(self.h, _dp(scan), slot_bytes, _dp(scan_bytes), nimg, C.byref(frame), int(gray), _dp(r), _dp(g),
+                                                  _dp(b), plane_len, _dp(status)))

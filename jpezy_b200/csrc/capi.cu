@@ -47,6 +47,7 @@ static void build_enc_lut(const HuffSpec& dc, const HuffSpec& ac, HuffEncLut* ou
 }
 
 static cudaStream_t pick_stream(jpezyb200_ctx* ctx, void* s) { return s ? static_cast<cudaStream_t>(s) : ctx->stream; }
+static void batch_pipe_destroy(jpezyb200_ctx* ctx);
 
 }  // namespace jz
 
@@ -157,6 +158,7 @@ void jpezyb200_ctx_destroy(jpezyb200_ctx* ctx)
     if (ctx->d_dec_lut) cudaFree(ctx->d_dec_lut);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_y_exact) cudaFree(ctx->d_y_exact);
+    jz::batch_pipe_destroy(ctx);
     std::free(ctx->shard_state);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -169,6 +171,10 @@ int jpezyb200_set_option(jpezyb200_ctx* ctx, int option, int64_t value)
     switch (option) {
     case JPEZYB200_OPT_PAD_ONES: ctx->pad_ones = value ? 1 : 0; return JPEZYB200_OK;
     case JPEZYB200_OPT_TRANSFORM: ctx->transform_variant = int(value); return JPEZYB200_OK;
+    case JPEZYB200_OPT_BATCH_GROUP_BYTES:
+        if (value < 1) return ctx->fail(JPEZYB200_EINVAL, "group bytes must be positive");
+        ctx->group_bytes = value;
+        return JPEZYB200_OK;
     case JPEZYB200_OPT_SYNC_ROUNDS:
         if (value < 0 || value > 64) return ctx->fail(JPEZYB200_EINVAL, "sync rounds must be in 0..64");
         ctx->sync_rounds = int(value);
@@ -388,3 +394,4 @@ int jpezyb200_synth_rows_dev(jpezyb200_ctx* ctx, uint8_t* d_r, uint8_t* d_g, uin
 
 #include "capi_decode.inc"
 #include "capi_shard.inc"
+#include "capi_batch.inc"

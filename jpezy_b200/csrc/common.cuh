@@ -61,6 +61,7 @@ struct jpezyb200_ctx {
     int pad_ones = 1;
     int transform_variant = 0;
     int sync_rounds = 3;
+    int64_t group_bytes = int64_t(96) << 20;   // host<->device bytes per stage of the pipelined host batches
     uint64_t launches = 0;
     bool inv_attr_set = false;
 
@@ -78,6 +79,7 @@ struct jpezyb200_ctx {
     jz_devbuf coefs, blk_off, tile_sum, tile_base, img_bits, ustream, ff_sum, ff_base, planes_in, planes_out, scan_io, sizes_io;
     jz_devbuf dec_scanbytes, dec_chunk_cnt, dec_chunk_base, dec_ubytes, dec_state, dec_dirty, dec_subblk, dec_dc, dec_status, dec_changed, dec_mcnt, dec_mbase, dec_seg;
     jz_devbuf shard_geom;      // ShardGeom + scratch of the MCU-row sharded encoder (enc_shard.cuh)
+    void* batch_pipe = nullptr;    // streams, events and double buffers of the pipelined host batches (capi_batch.inc)
     void* shard_state = nullptr;   // host copy of the launch parameters between the phases (capi_shard.inc)
     void* h_pinned = nullptr;
     size_t h_pinned_cap = 0;

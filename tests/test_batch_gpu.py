@@ -1,0 +1,65 @@
+"""-m gpu: the pipelined host-buffer batch entry points (jpezyb200_encode_batch / jpezyb200_decode_batch) must give exactly
+what the per-image calls give, for one group and for many (the three-stream pipeline with double buffers)."""
+import numpy as np
+import pytest
+import torch
+
+import jpezy_b200 as J
+from jpezy_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("group_bytes", [96 << 20, 1, 3 * 200 * 120 * 2])        # one group / one image per group / two per group
+@pytest.mark.parametrize("gray", [False, True])
+def test_batch_equals_per_image(ctx, oracle, group_bytes, gray):
+    W, H, N = 200, 120, 7
+    imgs = [J.synth.image(k % 3, W, H, frame=k) for k in range(N)]
+    r, g, b = (np.ascontiguousarray(np.stack([im[c] for im in imgs])) for c in range(3))
+    slot = max(W * H * 3, 10240)
+    scans = np.zeros((N, slot), dtype=np.uint8)
+    nbytes = np.zeros(N, dtype=np.uint64)
+    try:
+        ctx.set_option(capi.OPT_BATCH_GROUP_BYTES, group_bytes)
+        ctx.encode_batch(r, g, b, W, H, N, gray, scans, slot, nbytes)
+        frame = J.default_frame(W, H)
+        pl = capi.plane_bytes(frame)
+        R, G, B = (np.full((N, pl), 0x55, dtype=np.uint8) for _ in range(3))
+        st = np.full(N, -1, dtype=np.int32)
+        ctx.decode_batch(scans, slot, nbytes, N, frame, gray, R, G, B, pl, st)
+    finally:
+        ctx.set_option(capi.OPT_BATCH_GROUP_BYTES, 96 << 20)
+    assert (st == 0).all()
+    for k, im in enumerate(imgs):
+        want, _ = ctx.encode(im[0], im[1], im[2], W, H, gray=gray)
+        assert scans[k, : int(nbytes[k])].tobytes() == want
+        if k < 3:
+            assert want == oracle.encode(im[0], im[1], im[2], W, H, gray=gray, scan_only=True)
+        r0, g0, b0 = ctx.decode(want, frame, gray=gray)
+        assert (R[k] == r0).all() and (G[k] == g0).all() and (B[k] == b0).all()
+
+
+def test_batch_with_pinned_buffers_and_small_slots(ctx):
+    W, H, N = 320, 192, 12
+    npx = W * H
+    r, g, b = (torch.empty((N, H, W), dtype=torch.uint8).pin_memory() for _ in range(3))
+    for k in range(N):
+        im = J.synth.image(1, W, H, frame=k)         # noise: ~2.5 bit/px
+        for t, a in zip((r, g, b), im):
+            t[k].copy_(torch.from_numpy(a))
+    slot = 4096                                       # far too small: every image must report UINT64_MAX
+    scans = torch.zeros((N, slot), dtype=torch.uint8).pin_memory()
+    nbytes = np.zeros(N, dtype=np.uint64)
+    with pytest.raises(J.JpezyError) as e:
+        ctx.encode_batch(r, g, b, W, H, N, False, scans, slot, nbytes)
+    assert e.value.code == capi.ECAPACITY and (nbytes == np.iinfo(np.uint64).max).all()
+    slot = npx
+    scans = torch.zeros((N, slot), dtype=torch.uint8).pin_memory()
+    ctx.set_option(capi.OPT_BATCH_GROUP_BYTES, 3 * npx * 5)
+    try:
+        ctx.encode_batch(r, g, b, W, H, N, False, scans, slot, nbytes)
+    finally:
+        ctx.set_option(capi.OPT_BATCH_GROUP_BYTES, 96 << 20)
+    for k in (0, 5, 11):
+        want, _ = ctx.encode(r[k].numpy(), g[k].numpy(), b[k].numpy(), W, H)
+        assert scans[k, : int(nbytes[k])].numpy().tobytes() == want
