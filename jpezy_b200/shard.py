@@ -181,7 +181,11 @@ def encode_sharded_local(ctxs, planes, W, H, gray=False, dst_cap=None, device="c
     nb = torch.zeros(n, dtype=torch.int64, device=device)
     total = torch.zeros(1, dtype=torch.int64, device=device)
     ovf = torch.zeros(n, dtype=torch.int32, device=device)
-    st = torch.cuda.current_stream().cuda_stream
+    # one explicit stream for all emulated ranks: a NULL stream would select every context's own private stream, and the
+    # phases of different ranks must be ordered with each other
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    st = stream.cuda_stream
     shards = []
     for (row0, nrows) in parts:       # every rank holds only its own pixel rows
         y0, ny = pixel_rows(H, row0, nrows)
@@ -282,8 +286,10 @@ def decode_sharded_local(ctxs, scan, frame, gray=False, device="cuda"):
     vu = -(-((frame.height + 7) // 8) // vs)
     planes = torch.full((3, pl), 0xAA, dtype=torch.uint8, device=device)       # poisoned: every byte must be written or cleared
     d_scan = torch.from_numpy(np.frombuffer(scan, dtype=np.uint8).copy()).to(device)
-    st = torch.cuda.current_stream().cuda_stream
     status = torch.zeros(n, dtype=torch.int32, device=device)
+    stream = torch.cuda.Stream()          # (see encode_sharded_local)
+    torch.cuda.synchronize()
+    st = stream.cuda_stream
     for k, (row0, nrows) in enumerate(partition_mcu_rows(vu, n)):
         ctxs[k].shard_decode_dev(d_scan, len(scan), frame, gray, row0, nrows, planes[0], planes[1], planes[2], pl, status[k: k + 1], stream=st)
     torch.cuda.synchronize()

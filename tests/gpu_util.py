@@ -15,6 +15,7 @@ def gpu_coefs(ctx, r, g, b, W, H, gray=False, nimg=1):
     n = num_mcus(W, H)
     dc = torch.empty((nimg, n, 6, 64), dtype=torch.int16, device="cuda")
     dc.fill_(-12345)
+    torch.cuda.synchronize()      # torch's stream and the context's own (non-blocking) stream are not ordered with each other
     ctx.transform_fwd_dev(dr, dg, db, W, H, nimg, gray, dc, stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     return dc.cpu().numpy()
@@ -26,6 +27,7 @@ def gpu_entropy(ctx, coefs, W, H, nimg=1, slot=None):
     out = torch.zeros((nimg, slot), dtype=torch.uint8, device="cuda")
     nbytes = torch.zeros(nimg, dtype=torch.int64, device="cuda")
     nbits = torch.zeros(nimg, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
     ctx.entropy_encode_dev(dc, W, H, nimg, False, out, slot, nbytes, nbits, stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     nb = nbytes.cpu().numpy()

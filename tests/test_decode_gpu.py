@@ -33,6 +33,7 @@ def gpu_entropy_decode(ctx, scans, W, H):
     nm = capi.num_mcus(W, H)
     dc = torch.full((n, nm, 6, 64), 777, dtype=torch.int16, device="cuda")
     st = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()      # torch's stream and the context's own (non-blocking) stream are not ordered with each other
     ctx.entropy_decode_dev(d, slot, [len(s) for s in scans], n, frame, dc, st, stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     return dc.cpu().numpy(), st.cpu().numpy()

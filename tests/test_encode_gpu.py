@@ -148,6 +148,7 @@ def test_batch_encode_matches_single(ctx, oracle):
     slot = W * H * 3
     out = torch.zeros((N, slot), dtype=torch.uint8, device="cuda")
     nbytes = torch.zeros(N, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()      # torch's stream and the context's own (non-blocking) stream are not ordered with each other
     ctx.encode_batch_dev(R, G, B, W, H, N, False, out, slot, nbytes, None, stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     o, nb = out.cpu().numpy(), nbytes.cpu().numpy()
