@@ -8,9 +8,11 @@
 #define JPEZY_B200_ENCODE_IO_HPP
 
 #include <cctype>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <string>
+#include <string_view>
 #include <tuple>
 #include <utility>
 #include <vector>
@@ -31,53 +33,95 @@ inline constexpr gray_scale_t gray_scale{};
 struct encode_io : pnm_stream {
     encode_io(const char* file_name) : pnm_stream(true, 0, 0, 0)
     {
-        std::ifstream ifs(file_name);
-        if (!ifs) {
-            initializing_succeed = false;
-            return;
+        // the whole file in one read; lines are cut out of the buffer with std::getline's rules
+        std::string buf;
+        {
+            std::ifstream ifs(file_name, std::ios::binary);
+            if (!ifs) {
+                initializing_succeed = false;
+                return;
+            }
+            ifs.seekg(0, std::ios::end);
+            const std::streamoff n = ifs.tellg();
+            ifs.seekg(0, std::ios::beg);
+            if (n > 0) {
+                buf.resize(std::size_t(n));
+                ifs.read(&buf[0], n);
+                buf.resize(std::size_t(ifs.gcount()));
+            }
         }
+        std::size_t pos = 0;
+        bool eof = false;
+        // std::getline: a line ends at '\n'; reaching the end of the data while reading sets eof (and the text read so far
+        // is still a line); a call that extracts nothing fails and leaves an empty string
+        const auto getline = [&](std::string_view& out) {
+            if (pos >= buf.size()) {
+                eof = true;
+                out = std::string_view();
+                return false;
+            }
+            const void* nl = std::memchr(buf.data() + pos, '\n', buf.size() - pos);
+            if (nl) {
+                const std::size_t e = std::size_t(static_cast<const char*>(nl) - buf.data());
+                out = std::string_view(buf.data() + pos, e - pos);
+                pos = e + 1;
+            } else {
+                out = std::string_view(buf.data() + pos, buf.size() - pos);
+                pos = buf.size();
+                eof = true;
+            }
+            return true;
+        };
         // src/encoder/encode_io.hpp:50-56: read lines until one without '#' (or until getline fails; the last string read is returned)
-        const auto jump_comment = [&ifs]() {
-            std::string str;
-            while (std::getline(ifs, str) && str.find('#') != std::string::npos) {}
+        const auto jump_comment = [&]() {
+            std::string_view str;
+            while (getline(str) && str.find('#') != std::string_view::npos) {}
             return str;
         };
-        // boost::split(is_space()) with token_compress_off: every separator ends a token
-        const auto split = [](const std::string& s) {
-            std::vector<std::string> out(1);
-            for (char c : s) {
-                if (std::isspace(static_cast<unsigned char>(c))) out.emplace_back();
-                else out.back().push_back(c);
+        const auto is_space = [](char c) { return std::isspace(static_cast<unsigned char>(c)) != 0; };
+        // std::stoi on one token; all-digit tokens (every token of a well-formed file) take a short cut
+        const auto to_int = [](std::string_view tok) -> int {
+            if (!tok.empty() && tok.size() <= 9) {
+                int v = 0;
+                std::size_t i = 0;
+                for (; i < tok.size() && tok[i] >= '0' && tok[i] <= '9'; ++i) v = v * 10 + (tok[i] - '0');
+                if (i == tok.size()) return v;
             }
-            return out;
+            return std::stoi(std::string(tok));       // "" -> std::invalid_argument, "12x" -> 12, as in the reference
         };
-        std::string format = jump_comment();
+        // boost::split(is_space()) with token_compress_off: every separator ends a token
+        const auto for_each_token = [&](std::string_view line, auto&& f) {
+            std::size_t i = 0;
+            for (;;) {
+                std::size_t j = i;
+                while (j < line.size() && !is_space(line[j])) ++j;
+                const bool last = j >= line.size();
+                f(line.substr(i, j - i), last);
+                if (last) break;
+                i = j + 1;
+            }
+        };
+        std::string_view format = jump_comment();
         if (format != "P3") {
             initializing_succeed = false;
             return;
         }
         format = jump_comment();
-        const std::vector<std::string> wh = split(format);
+        std::vector<std::string_view> wh;
+        for_each_token(format, [&](std::string_view t, bool) { wh.push_back(t); });
         if (wh.size() != 2) {
             initializing_succeed = false;
         } else {
-            width = std::size_t(std::stoi(wh[0])), height = std::size_t(std::stoi(wh[1]));
+            width = std::size_t(to_int(wh[0])), height = std::size_t(to_int(wh[1]));
             format = jump_comment();
-            max_color = std::size_t(std::stoi(format));
+            max_color = std::size_t(std::stoi(std::string(format)));      // whole line through stoi (leading blanks allowed)
             std::vector<value_type> img;
             img.reserve(width * height * 3);
-            for (std::string line = jump_comment(); !ifs.eof(); line = jump_comment()) {
-                // tokens of the line; exactly one trailing empty token is forgiven (:83-84), every other one reaches stoi
-                std::size_t i = 0;
-                const std::size_t n = line.size();
-                for (;;) {
-                    std::size_t j = i;
-                    while (j < n && !std::isspace(static_cast<unsigned char>(line[j]))) ++j;
-                    const bool last = j >= n;
-                    if (!(last && j == i)) img.push_back(value_type(std::stoi(line.substr(i, j - i))));   // "" -> std::invalid_argument
-                    if (last) break;
-                    i = j + 1;
-                }
+            for (std::string_view line = jump_comment(); !eof; line = jump_comment()) {
+                // exactly one trailing empty token is forgiven (:83-84), every other one reaches stoi
+                for_each_token(line, [&](std::string_view t, bool last) {
+                    if (!(last && t.empty())) img.push_back(value_type(to_int(t)));
+                });
             }
             rgb_img.resize(img.size() / 3);
             for (std::size_t k = 0; k < rgb_img.size(); ++k) rgb_img[k] = {img[3 * k], img[3 * k + 1], img[3 * k + 2]};
@@ -90,8 +134,16 @@ private:
     friend std::ostream& operator<<(std::ostream& os, const encode_io& pnm)
     {
         pnm.report_error(__func__);
-        os << "P3\n" << pnm.width << " " << pnm.height << "\n" << pnm.max_color << "\n";
-        for (const auto& rgb : pnm.rgb_img) os << unsigned(rgb[0]) << " " << unsigned(rgb[1]) << " " << unsigned(rgb[2]) << '\n';
+        std::string out = "P3\n" + std::to_string(pnm.width) + " " + std::to_string(pnm.height) + "\n" + std::to_string(pnm.max_color) + "\n";
+        out.reserve(out.size() + pnm.rgb_img.size() * 12);
+        const auto put = [&out](unsigned v, char sep) {
+            if (v >= 100) out.push_back(char('0' + v / 100));
+            if (v >= 10) out.push_back(char('0' + v / 10 % 10));
+            out.push_back(char('0' + v % 10));
+            out.push_back(sep);
+        };
+        for (const auto& rgb : pnm.rgb_img) put(rgb[0], ' '), put(rgb[1], ' '), put(rgb[2], '\n');
+        os.write(out.data(), std::streamsize(out.size()));
         return os;
     }
 

@@ -63,6 +63,8 @@ PPM_CASES = {
     "no_final_newline_drops_last_line": "P3\n2 2\n255\n1 2 3\n4 5 6\n7 8 9\n10 11 12",
     "trailing_blank_and_crlf": "P3\n2 2\n255\n1 2 3 \n4 5 6\r\n7 8 9 10 11 12\n",
     "values_wrap_mod_256": "P3\n1 1\n65535\n256 511 1000\n",
+    "stoi_oddities": "P3\n2 2\n 255\n+5 12x -1\n\n7\t8 9\n010 0x10 99999999999\n1 2 3\n",
+    "interior_empty_token_throws": "P3\n1 1\n255\n1  2 3\n",
     "not_p3": "P6\n1 1\n255\n1 2 3\n",
     "size_line_three_tokens": "P3\n2 2 \n255\n1 2 3\n",
 }
