@@ -55,6 +55,8 @@ using namespace jz;
 
 extern "C" {
 
+static void host_pipe_destroy(jpezyb200_ctx* ctx);
+
 int jpezyb200_abi_version(void) { return JPEZYB200_ABI_VERSION; }
 
 const char* jpezyb200_strerror(int code)
@@ -159,6 +161,7 @@ void jpezyb200_ctx_destroy(jpezyb200_ctx* ctx)
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_y_exact) cudaFree(ctx->d_y_exact);
     jz::batch_pipe_destroy(ctx);
+    host_pipe_destroy(ctx);
     std::free(ctx->shard_state);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -203,6 +206,46 @@ int jpezyb200_get_stat(jpezyb200_ctx* ctx, int stat, uint64_t* value)
 // -------------------------------------------------------------------------------------------------
 // encoder
 // -------------------------------------------------------------------------------------------------
+// copy stream + events of the band-pipelined single-image host entry points (jpezyb200_encode / jpezyb200_decode)
+constexpr int kHostBands = 8;
+// bands of MCU rows whose copies overlap the transform kernels.  Measured on a 4K frame: 1 band 6.48 GPix/s, 2: 6.49, 3: 6.44,
+// 4: 6.34, 8: 6.23 -- the round trip is bound by the two 25 MB PCIe copies, the 77 us of transform time that could hide behind
+// them do not pay for the extra copy calls.  Default 1 (JPEZY_B200_HOST_BANDS overrides, for experiments).
+static size_t host_bands()
+{
+    static const size_t n = [] { const char* e = std::getenv("JPEZY_B200_HOST_BANDS"); const long v = e ? std::atol(e) : 1; return size_t(v < 1 ? 1 : (v > kHostBands ? kHostBands : v)); }();
+    return n;
+}
+struct HostPipe {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev[kHostBands] = {};
+    uint64_t* h_sz = nullptr;      // pinned: sizes / status read back by the host
+};
+static int host_pipe(jpezyb200_ctx* ctx, HostPipe** out)
+{
+    if (!ctx->host_pipe) {
+        HostPipe* hp = new (std::nothrow) HostPipe();
+        if (!hp) return JPEZYB200_ENOMEM;
+        ctx->host_pipe = hp;
+        JZ_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&hp->copy, cudaStreamNonBlocking));
+        for (cudaEvent_t& e : hp->ev) JZ_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        JZ_CUDA_TRY(ctx, cudaMallocHost(&hp->h_sz, 64));
+    }
+    *out = static_cast<HostPipe*>(ctx->host_pipe);
+    return JPEZYB200_OK;
+}
+static void host_pipe_destroy(jpezyb200_ctx* ctx)
+{
+    HostPipe* hp = static_cast<HostPipe*>(ctx->host_pipe);
+    if (!hp) return;
+    if (hp->copy) cudaStreamSynchronize(hp->copy), cudaStreamDestroy(hp->copy);
+    for (cudaEvent_t e : hp->ev)
+        if (e) cudaEventDestroy(e);
+    if (hp->h_sz) cudaFreeHost(hp->h_sz);
+    delete hp;
+    ctx->host_pipe = nullptr;
+}
+
 static int check_geometry(jpezyb200_ctx* ctx, uint32_t W, uint32_t H, uint32_t nimg)
 {
     if (!ctx) return JPEZYB200_EINVAL;
@@ -212,17 +255,18 @@ static int check_geometry(jpezyb200_ctx* ctx, uint32_t W, uint32_t H, uint32_t n
     return JPEZYB200_OK;
 }
 
+// rows: MCU rows [row0, row0 + nrows) only (nrows == 0: all); the planes always hold the whole image
 static int launch_fwd(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g, const uint8_t* d_b, uint32_t W, uint32_t H,
-                      uint32_t nimg, int gray, int16_t* d_coefs, cudaStream_t st)
+                      uint32_t nimg, int gray, int16_t* d_coefs, cudaStream_t st, uint32_t row0 = 0, uint32_t nrows = 0)
 {
     FwdParams p{};
     p.r = d_r, p.g = d_g, p.b = d_b;
     p.plane_stride = size_t(W) * H;
     p.W = W, p.H = H;
-    p.HU = mcu_units(W), p.VU = mcu_units(H);
-    p.coefs = d_coefs;
-    p.coef_stride = size_t(p.HU) * p.VU * 384;
-    p.row0 = 0, p.y_origin = 0;
+    p.HU = mcu_units(W), p.VU = nrows ? nrows : mcu_units(H);
+    p.coefs = d_coefs + size_t(row0) * p.HU * 384;
+    p.coef_stride = size_t(p.HU) * mcu_units(H) * 384;
+    p.row0 = row0, p.y_origin = 0;
     p.gray = gray;
     p.guard_counter = ctx->d_counters + 0;
     p.y_exact = ctx->d_y_exact;
@@ -334,20 +378,36 @@ int jpezyb200_encode(jpezyb200_ctx* ctx, const uint8_t* r, const uint8_t* g, con
     if (!r || !g || !b || !scan_out || !scan_bytes || scan_cap == 0) return ctx->fail(JPEZYB200_EINVAL, "null pointer / empty buffer");
     JZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t npx = size_t(W) * H;
+    const uint32_t HU = mcu_units(W), VU = mcu_units(H);
     if ((rc = ctx->ensure(ctx->planes_in, 3 * npx))) return rc;
     if ((rc = ctx->ensure(ctx->scan_io, scan_cap))) return rc;
     if ((rc = ctx->ensure(ctx->sizes_io, 64))) return rc;
+    if ((rc = ctx->ensure(ctx->coefs, size_t(HU) * VU * 384 * sizeof(int16_t)))) return rc;
     uint8_t* d_in = static_cast<uint8_t*>(ctx->planes_in.p);
     uint64_t* d_sz = static_cast<uint64_t*>(ctx->sizes_io.p);
+    int16_t* d_coefs = static_cast<int16_t*>(ctx->coefs.p);
     cudaStream_t st = ctx->stream;
-    JZ_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, r, npx, cudaMemcpyHostToDevice, st));
-    JZ_CUDA_TRY(ctx, cudaMemcpyAsync(d_in + npx, g, npx, cudaMemcpyHostToDevice, st));
-    JZ_CUDA_TRY(ctx, cudaMemcpyAsync(d_in + 2 * npx, b, npx, cudaMemcpyHostToDevice, st));
-    rc = jpezyb200_encode_batch_dev(ctx, d_in, d_in + npx, d_in + 2 * npx, W, H, 1, gray, static_cast<uint8_t*>(ctx->scan_io.p),
-                                    scan_cap, d_sz, d_sz + 1, st);
-    if (rc) return rc;
-    uint64_t h_sz[2] = {0, 0};
-    JZ_CUDA_TRY(ctx, cudaMemcpyAsync(h_sz, d_sz, sizeof h_sz, cudaMemcpyDeviceToHost, st));
+    // bands of MCU rows: the copy of band k+1 (copy stream) overlaps the transform of band k (compute stream)
+    HostPipe* hp;
+    if ((rc = host_pipe(ctx, &hp))) return rc;
+    const uint32_t nband = uint32_t(std::max<size_t>(1, std::min<size_t>(std::min<size_t>(host_bands(), VU), 3 * npx / (size_t(4) << 20))));
+    for (uint32_t k = 0; k < nband; ++k) {
+        const uint32_t row0 = uint32_t(uint64_t(VU) * k / nband), row1 = uint32_t(uint64_t(VU) * (k + 1) / nband);
+        const size_t y0 = std::min<size_t>(H, size_t(row0) * 16), y1 = std::min<size_t>(H, size_t(row1) * 16);
+        // (edge replication reads the last image row: the last band carries it)
+        const size_t off = y0 * W, len = (y1 - y0) * W;
+        if (len) {
+            JZ_CUDA_TRY(ctx, cudaMemcpyAsync(d_in + off, r + off, len, cudaMemcpyHostToDevice, hp->copy));
+            JZ_CUDA_TRY(ctx, cudaMemcpyAsync(d_in + npx + off, g + off, len, cudaMemcpyHostToDevice, hp->copy));
+            JZ_CUDA_TRY(ctx, cudaMemcpyAsync(d_in + 2 * npx + off, b + off, len, cudaMemcpyHostToDevice, hp->copy));
+        }
+        JZ_CUDA_TRY(ctx, cudaEventRecord(hp->ev[k], hp->copy));
+        JZ_CUDA_TRY(ctx, cudaStreamWaitEvent(st, hp->ev[k], 0));
+        if ((rc = launch_fwd(ctx, d_in, d_in + npx, d_in + 2 * npx, W, H, 1, gray, d_coefs, st, row0, row1 - row0))) return rc;
+    }
+    if ((rc = launch_entropy(ctx, d_coefs, W, H, 1, static_cast<uint8_t*>(ctx->scan_io.p), scan_cap, d_sz, d_sz + 1, st))) return rc;
+    uint64_t* h_sz = hp->h_sz;
+    JZ_CUDA_TRY(ctx, cudaMemcpyAsync(h_sz, d_sz, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     JZ_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     if (h_sz[0] == ~0ull || h_sz[0] > scan_cap) return ctx->fail(JPEZYB200_ECAPACITY, "entropy-coded segment does not fit in scan_cap");
     JZ_CUDA_TRY(ctx, cudaMemcpyAsync(scan_out, ctx->scan_io.p, h_sz[0], cudaMemcpyDeviceToHost, st));

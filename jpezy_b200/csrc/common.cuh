@@ -80,6 +80,7 @@ struct jpezyb200_ctx {
     jz_devbuf dec_scanbytes, dec_chunk_cnt, dec_chunk_base, dec_ubytes, dec_state, dec_dirty, dec_subblk, dec_dc, dec_status, dec_changed, dec_mcnt, dec_mbase, dec_seg;
     jz_devbuf shard_geom;      // ShardGeom + scratch of the MCU-row sharded encoder (enc_shard.cuh)
     void* batch_pipe = nullptr;    // streams, events and double buffers of the pipelined host batches (capi_batch.inc)
+    void* host_pipe = nullptr;     // copy stream and events of the band-pipelined single-image host entry points (capi.cu)
     void* shard_state = nullptr;   // host copy of the launch parameters between the phases (capi_shard.inc)
     void* h_pinned = nullptr;
     size_t h_pinned_cap = 0;
