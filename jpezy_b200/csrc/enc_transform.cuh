@@ -339,6 +339,65 @@ __device__ __forceinline__ void aan_fdct8(float& d0, float& d1, float& d2, float
     d7 = z11 - z4;
 }
 
+// ---- packed FP32 pairs (FADD2 / FMUL2 / FFMA2 of sm_100): two rows of a block go through the row pass at once; every
+// lane of a pair is an ordinary IEEE add / mul / fma, so the results equal the scalar flowgraph's bit for bit ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// aan_fdct8 on two independent 8-vectors at once (same operation order)
+__device__ __forceinline__ void aan_fdct8_x2(f32x2& d0, f32x2& d1, f32x2& d2, f32x2& d3, f32x2& d4, f32x2& d5, f32x2& d6, f32x2& d7)
+{
+    const f32x2 c707 = pk2(0.707106781186547524f, 0.707106781186547524f), c382 = pk2(0.382683432365089772f, 0.382683432365089772f);
+    const f32x2 c541 = pk2(0.541196100146196985f, 0.541196100146196985f), c1306 = pk2(1.306562964876376528f, 1.306562964876376528f);
+    const f32x2 t0 = add2(d0, d7), t7 = sub2(d0, d7), t1 = add2(d1, d6), t6 = sub2(d1, d6);
+    const f32x2 t2 = add2(d2, d5), t5 = sub2(d2, d5), t3 = add2(d3, d4), t4 = sub2(d3, d4);
+    const f32x2 t10 = add2(t0, t3), t13 = sub2(t0, t3), t11 = add2(t1, t2), t12 = sub2(t1, t2);
+    d0 = add2(t10, t11);
+    d4 = sub2(t10, t11);
+    const f32x2 z1 = mul2(add2(t12, t13), c707);
+    d2 = add2(t13, z1);
+    d6 = sub2(t13, z1);
+    const f32x2 u10 = add2(t4, t5), u11 = add2(t5, t6), u12 = add2(t6, t7);
+    const f32x2 z5 = mul2(sub2(u10, u12), c382);
+    const f32x2 z2 = fma2(u10, c541, z5);
+    const f32x2 z4 = fma2(u12, c1306, z5);
+    const f32x2 z3 = mul2(u11, c707);
+    const f32x2 z11 = add2(t7, z3), z13 = sub2(t7, z3);
+    d5 = add2(z13, z2);
+    d3 = sub2(z13, z2);
+    d1 = add2(z11, z4);
+    d7 = sub2(z11, z4);
+}
+
 // Fix-up queue: coefficients whose FP32 value is inside the guard band are not decided in the hot loop;
 // (block, natural index) is pushed to shared memory and the whole CTA re-evaluates the queue afterwards.
 constexpr int kFixCap = 1024;
@@ -533,11 +592,25 @@ __global__ void __launch_bounds__(256, 2) k_fwd_transform(const FwdParams p)
             d[y * 8 + 4] = float(w.y & 255u), d[y * 8 + 5] = float((w.y >> 8) & 255u);
             d[y * 8 + 6] = float((w.y >> 16) & 255u), d[y * 8 + 7] = float(w.y >> 24);
         }
+        // row pass: rows 2k and 2k+1 as packed pairs; column pass: columns 2k and 2k+1 as packed pairs
 #pragma unroll
-        for (int y = 0; y < 8; ++y)
-            aan_fdct8(d[y * 8 + 0], d[y * 8 + 1], d[y * 8 + 2], d[y * 8 + 3], d[y * 8 + 4], d[y * 8 + 5], d[y * 8 + 6], d[y * 8 + 7]);
+        for (int k = 0; k < 4; ++k) {
+            f32x2 q[8];
 #pragma unroll
-        for (int x = 0; x < 8; ++x) aan_fdct8(d[x], d[8 + x], d[16 + x], d[24 + x], d[32 + x], d[40 + x], d[48 + x], d[56 + x]);
+            for (int x = 0; x < 8; ++x) q[x] = pk2(d[(2 * k) * 8 + x], d[(2 * k + 1) * 8 + x]);
+            aan_fdct8_x2(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]);
+#pragma unroll
+            for (int x = 0; x < 8; ++x) unpk2(q[x], d[(2 * k) * 8 + x], d[(2 * k + 1) * 8 + x]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            f32x2 q[8];
+#pragma unroll
+            for (int y = 0; y < 8; ++y) q[y] = pk2(d[y * 8 + 2 * k], d[y * 8 + 2 * k + 1]);
+            aan_fdct8_x2(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]);
+#pragma unroll
+            for (int y = 0; y < 8; ++y) unpk2(q[y], d[y * 8 + 2 * k], d[y * 8 + 2 * k + 1]);
+        }
         d[0] -= 8192.0f;   // level shift: the samples are stored as value + 128 (64 * 128, exact)
         uint4* out16 = reinterpret_cast<uint4*>(&s_out[blk * kOutStride]);
         if (warp < 4) quant_block<0>(d, blk, &s_nfix, s_fix, out16);
