@@ -105,6 +105,7 @@ int jpezyb200_ctx_create(int device, jpezyb200_ctx** out)
         }
         h.inv_sqrt2_ref = kInvSqrt2Ref;
         JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(cC, &h, sizeof h));
+        JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(gCosRef, h.cos_ref, sizeof h.cos_ref));
         {
             // constants of the FP32 AAN path: K folds the AAN scale factors, the /8 and 1/q; G is the guard band
             // (1.25 x worst-case flowgraph error + the rounding of w itself) in w units; T the "quantises to 0" test

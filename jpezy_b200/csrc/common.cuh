@@ -23,6 +23,9 @@ struct DevConst {
     uint8_t izz[64];       // natural position -> zig-zag position
 };
 static __constant__ DevConst cC;   // single translation unit (capi.cu)
+// the same cosine table in global memory, for the fix-up phases whose lanes index it divergently (a constant-bank
+// load serialises per distinct address; an L1 load does not)
+static __device__ double gCosRef[64];
 
 // Huffman encoder LUT, one per table class (0 = luma tables, 1 = chroma tables).
 // ac[(run << 4) | size] and dc[category]; entry = (code << 5) | length, 0 = invalid.

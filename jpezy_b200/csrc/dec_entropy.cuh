@@ -27,11 +27,17 @@ constexpr int kLutBits = 10;
 
 // compact canonical decoder table for one DHT table, built on the host
 // entry of the decoder tables (0 = no code of at most kLutBits bits starts here):
-//   bits 0..4   code length + size of the value field = bits to consume
+//   bits 0..4   bits to consume: code length + size of the value field (+ the end-of-block code, see bit 5)
+//   bit  5      the end-of-block code of the block's AC table follows inside the kLutBits window and is consumed with
+//               this symbol: one table access instead of two for "DC difference, EOB" and "coefficient, EOB" (most
+//               blocks of photographic content).  Not valid when the symbol itself fills the block (z + dz >= 64: the
+//               bits that look like EOB then belong to the next block) -- the decoders give bits 25..28 back.
 //   bits 8..14  dz: advance of the zig-zag index; DC tables: 1; AC tables: run + 1, end-of-block: 64 (so that z + dz >= 64
 //               closes the block in both cases; ZRL = (15, 0) advances by 16 like the generic path of the reference,
 //               src/decoder/jpezy_decoder.hpp:611-622)
 //   bits 16..20 code length, bits 21..24 size (value extraction in the writing pass)
+//   bits 25..28 length of the end-of-block code folded in (bit 5)
+constexpr uint32_t kEntryEob = 32u;
 __host__ __device__ inline uint32_t huff_entry(uint32_t len, uint32_t sym, bool ac)
 {
     const uint32_t size = sym & 15u, run = sym >> 4;
@@ -49,6 +55,11 @@ struct HuffDecTab {
     HuffSlow slow;                 // slow.pad_ = 1 for AC tables
 };
 static_assert(sizeof(HuffSlow) % 4 == 0 && sizeof(HuffDecTab) % 16 == 0, "copied to shared memory in words / 16-byte chunks");
+// the four tables of a scan as the kernels keep them in shared memory
+struct DecTabs {
+    uint32_t fast[4][1 << kLutBits];
+    HuffSlow slow[4];
+};
 
 struct DecParams {
     // geometry
@@ -76,6 +87,7 @@ struct DecParams {
     uint64_t* seg_start;      // [nimg][nseg + 1] first un-stuffed byte of every segment (segment 0: 0)
     // synchronisation
     uint32_t sub_bits;        // subsequence length in bits (128, 256 or 512)
+    uint32_t cta_own;         // subsequences a CTA of k_sync_decode / k_write_coefs owns: its threads minus kDecWarm (96 or 224)
     uint32_t nsub;            // subsequences per image (capacity)
     uint32_t* sub_state;      // [nimg][nsub] packed end state of every subsequence
     uint32_t* state_a;        // [nimg][ncta] CTA tail states, double buffered across launches
@@ -148,34 +160,87 @@ __device__ __noinline__ uint32_t huff_lookup_slow(const HuffSlow* __restrict__ t
     return 0;
 }
 
+// ---- the reader of the synchronisation / writing passes ------------------------------------------------------
+// Same span, but the words are staged byte-swapped (big-endian bit order in every word), and 96 bits are buffered in
+// registers: with 64 <= n <= 96 before a symbol is consumed and at most 31 bits per symbol, the top word is
+// completely valid after the shift whether or not a refill follows.  The table index of the NEXT symbol therefore
+// hangs off one funnel shift of `hi`, and the refill (mid / lo / nxt only) stays off the dependent chain
+// symbol -> length -> shift -> index -> table word, which is what bounds a thread's decode rate.
+struct FastBits {
+    const uint32_t* base;   // the span
+    const uint32_t* w;      // next word to pre-load (shared memory, byte-swapped words)
+    uint32_t hi, mid, lo, nxt;
+    int n;               // valid bits in hi:mid:lo
+    uint32_t pos;        // bit position of the first bit of hi, relative to the span
+    __device__ __forceinline__ void init(const uint32_t* span, uint32_t p)
+    {
+        base = span;
+        w = span + (p >> 5);
+        const uint32_t a = w[0], b = w[1], c = w[2];
+        nxt = w[3];
+        w += 4;
+        const uint32_t sh = p & 31u;
+        hi = __funnelshift_l(b, a, sh), mid = __funnelshift_l(c, b, sh), lo = c << sh;
+        n = 96 - int(sh);
+        pos = p;
+    }
+    // drop k <= 31 bits (only the low 5 bits of k are looked at) and top the buffer up; `hi` is final after the first line
+    __device__ __forceinline__ void consume(uint32_t k)
+    {
+        hi = __funnelshift_l(mid, hi, k);
+        mid = __funnelshift_l(lo, mid, k);
+        lo <<= (k & 31u);
+        n -= int(k & 31u);
+        pos += k & 31u;
+        const bool rf = n < 64;                       // then lo is empty and 33 <= n: append nxt behind bit n
+        const uint32_t s = uint32_t(n) & 31u;         // n - 32 for 33..63
+        const uint32_t add_mid = s ? nxt >> s : 0u;   // (n == 32 cannot happen with k <= 31; s == 0 only at n == 64)
+        mid |= rf ? add_mid : 0u;
+        lo = rf ? nxt << ((32u - s) & 31u) : lo;
+        if (rf) nxt = *w++;
+        n += rf ? 32 : 0;
+    }
+};
+
 // Decode from (br.pos, b, z) until br.pos >= end (or >= limit); positions are relative to the span.  With kWrite the
 // coefficients that carry a value field are stored (the buffer is pre-zeroed), block ordinals start at blk.
-// s_fast: [0] = DC class 0 (luma), [1] = DC class 1, [2] = AC class 0, [3] = AC class 1 (contiguous)
+// s_fast: [0] = DC class 0 (luma), [1] = DC class 1, [2] = AC class 0, [3] = AC class 1 (contiguous).
+// The next symbol comes from the AC table of the block's class, or, if this symbol closes the block, from the DC table
+// of the next block's class: both words are fetched as soon as the index is known and the block-end test selects.
 template <bool kWrite>
-__device__ __forceinline__ void decode_span(BitBuf& br, uint32_t& b, uint32_t& z, uint32_t& nblocks, const uint32_t end,
-                                            const uint32_t limit, const HuffSlow* __restrict__ slow,
-                                            const uint32_t (*s_fast)[1 << kLutBits], int16_t* __restrict__ out, uint64_t blk,
+__device__ __forceinline__ void decode_span(FastBits& br, uint32_t& b, uint32_t& z, uint32_t& nblocks, const uint32_t end,
+                                            const uint32_t limit, const DecTabs* __restrict__ T, int16_t* __restrict__ out, uint64_t blk,
                                             const uint64_t nblk, int* corrupt, const uint32_t nb, const uint32_t ny)
 {
     const uint32_t stop = end < limit ? end : limit;
-    // table of the next symbol: DC table of the block's class at z == 0, else the AC table of the same class
-    uint32_t ti = (z == 0u ? 0u : 2u) + (b >= ny ? 1u : 0u);
+    const uint32_t* tab = &T->fast[0][0];
+    uint32_t bn = (b + 1u == nb) ? 0u : b + 1u;                       // the block after this one
+    uint32_t t_cont = (2u + (b >= ny ? 1u : 0u)) << kLutBits;         // AC table of this block
+    uint32_t t_new = (bn >= ny ? 1u : 0u) << kLutBits;                // DC table of the next block
+    uint32_t e = tab[(z == 0u ? ((b >= ny ? 1u : 0u) << kLutBits) : t_cont) + (br.hi >> (32 - kLutBits))];
     while (br.pos < stop) {
-        br.refill();
-        const uint32_t w = br.peek32();
-        uint32_t e = s_fast[ti][w >> (32 - kLutBits)];
-        if (e == 0u) {
-            e = huff_lookup_slow(slow + ti, w);
+        if (e == 0u) {             // code longer than kLutBits, or none
+            const uint32_t ti = (z == 0u ? 0u : 2u) + (b >= ny ? 1u : 0u);
+            e = huff_lookup_slow(T->slow + ti, br.hi);
             if (e == 0u) {         // no such code: only legal while speculating
                 if (kWrite && corrupt) *corrupt = 1;
-                br.skip(1);
+                br.consume(1);
+                e = tab[(ti << kLutBits) + (br.hi >> (32 - kLutBits))];
                 continue;
             }
         }
-        br.skip(int(e & 31u));     // code + value field <= 31 bits and the buffer holds >= 32
+        const uint32_t w = br.hi;
+        br.consume(e);             // code + value field (+ folded EOB) <= 31 bits
+        uint32_t idx = br.hi >> (32 - kLutBits);
+        uint32_t ea = tab[t_cont + idx], eb = tab[t_new + idx];
         const uint32_t dz = (e >> 8) & 127u;
+        if ((e & kEntryEob) && z + dz >= 64u) {                // the symbol filled the block: the "EOB" bits are the next block's
+            br.init(br.base, br.pos - ((e >> 25) & 15u));
+            idx = br.hi >> (32 - kLutBits);
+            ea = tab[t_cont + idx], eb = tab[t_new + idx];
+        }
         if (kWrite) {
-            const uint32_t len = (e >> 16) & 31u, sz = e >> 21;
+            const uint32_t len = (e >> 16) & 31u, sz = (e >> 21) & 15u;
             const uint32_t k = z + dz - 1u;                    // zig-zag index of this coefficient
             if (k > 63u && dz != 64u) {                        // run past the end of the block (src/decoder/jpezy_decoder.hpp:619)
                 if (corrupt) *corrupt = 1;
@@ -186,29 +251,30 @@ __device__ __forceinline__ void decode_span(BitBuf& br, uint32_t& b, uint32_t& z
                 out[blk * 64 + k] = int16_t(v);
             }
         }
-        z += dz;
-        ti |= 2u;                  // after the DC symbol: the AC table of the same class
-        if (z >= 64u) {
-            z = 0;
-            b = (b + 1u == nb) ? 0u : b + 1u;
-            ++nblocks;
-            ++blk;
-            if (kWrite && blk >= nblk) return;
-            ti = b >= ny ? 1u : 0u;
-        }
+        const bool endb = z + dz >= 64u || (e & kEntryEob);
+        z = endb ? 0u : z + dz;
+        e = endb ? eb : ea;
+        b = endb ? bn : b;
+        nblocks += endb ? 1u : 0u;
+        blk += endb ? 1u : 0u;
+        if (kWrite && blk >= nblk) return;
+        bn = (b + 1u == nb) ? 0u : b + 1u;
+        t_cont = (2u + (b >= ny ? 1u : 0u)) << kLutBits;
+        t_new = (bn >= ny ? 1u : 0u) << kLutBits;
     }
 }
 
-__device__ __forceinline__ void load_dec_tabs(const HuffDecTab* __restrict__ tabs, uint32_t (*s_fast)[1 << kLutBits], HuffSlow* s_slow)
+__device__ __forceinline__ void load_dec_tabs(const HuffDecTab* __restrict__ tabs, DecTabs* __restrict__ T)
 {
     constexpr int kFast16 = (1 << kLutBits) * 4 / 16, kSlowW = int(sizeof(HuffSlow) / 4);
     for (int i = threadIdx.x; i < 4 * kFast16; i += blockDim.x)
-        reinterpret_cast<uint4*>(s_fast[i / kFast16])[i % kFast16] = __ldg(reinterpret_cast<const uint4*>(tabs[i / kFast16].fast) + i % kFast16);
+        reinterpret_cast<uint4*>(T->fast[i / kFast16])[i % kFast16] = __ldg(reinterpret_cast<const uint4*>(tabs[i / kFast16].fast) + i % kFast16);
     for (int i = threadIdx.x; i < 4 * kSlowW; i += blockDim.x)
-        reinterpret_cast<uint32_t*>(&s_slow[i / kSlowW])[i % kSlowW] = __ldg(reinterpret_cast<const uint32_t*>(&tabs[i / kSlowW].slow) + i % kSlowW);
+        reinterpret_cast<uint32_t*>(&T->slow[i / kSlowW])[i % kSlowW] = __ldg(reinterpret_cast<const uint32_t*>(&tabs[i / kSlowW].slow) + i % kSlowW);
 }
 
-// stage the CTA's span of the un-stuffed stream: bytes [byte0, byte0 + span_bytes + kSpanSlack), 16-byte chunks
+// stage the CTA's span of the un-stuffed stream: bytes [byte0, byte0 + span_bytes + kSpanSlack), 16-byte chunks, as
+// byte-swapped words (FastBits)
 // (the stream buffer carries >= 128 bytes of zero slack behind the data and its slots are 16-byte aligned)
 __device__ __forceinline__ void load_span(const uint8_t* __restrict__ ustream, uint64_t byte0, uint32_t span_bytes, uint64_t uslot, uint32_t* s_span)
 {
@@ -216,7 +282,12 @@ __device__ __forceinline__ void load_span(const uint8_t* __restrict__ ustream, u
     uint4* dst = reinterpret_cast<uint4*>(s_span);
     const uint32_t n16 = (span_bytes + kSpanSlack) / 16;
     const uint64_t avail16 = (uslot - byte0) / 16;        // the last CTA's span reaches past the image's slot: zeros there
-    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = i < avail16 ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) {
+        uint4 v = i < avail16 ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+        v.x = __byte_perm(v.x, 0, 0x0123), v.y = __byte_perm(v.y, 0, 0x0123);      // big-endian bit order inside every word
+        v.z = __byte_perm(v.z, 0, 0x0123), v.w = __byte_perm(v.w, 0, 0x0123);
+        dst[i] = v;
+    }
 }
 
 // ---- D0: un-stuffing -------------------------------------------------------------------------------
@@ -358,13 +429,11 @@ __global__ void __launch_bounds__(kDecThreads) k_unstuff_write(const DecParams p
 // Launch k >= 1: the first owned subsequence is re-seeded from the previous CTA's last end state of launch k - 1
 // (`tail`); `changed` counts the end states that changed during a launch, 0 = global fixed point (normally launch 1).
 constexpr int kDecWarm = 32;
-constexpr int kDecOwn = kDecThreads - kDecWarm;
 
 __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, const int launch, const int host_poll)
 {
     extern __shared__ __align__(16) uint32_t s_span[];      // (kDecThreads * sub_bits / 8 + kSpanSlack) bytes of the stream
-    __shared__ __align__(16) uint32_t s_fast[4][1 << kLutBits];
-    __shared__ __align__(16) HuffSlow s_slow[4];
+    __shared__ __align__(16) DecTabs s_tabs;
     __shared__ uint32_t s_state[kDecThreads];
     __shared__ uint8_t s_chg[2][kDecThreads];
     // launches are enqueued without host round trips: once a launch saw no change (a global fixed point), the
@@ -374,7 +443,8 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     const size_t img = blockIdx.y;
     const uint64_t total_bits = p.ubytes[img] * 8;
     const int t = threadIdx.x;
-    const uint32_t first_own = blockIdx.x * kDecOwn;                                   // first owned subsequence
+    const uint32_t nthr = p.cta_own + kDecWarm;                                          // == blockDim.x
+    const uint32_t first_own = blockIdx.x * p.cta_own;                                   // first owned subsequence
     const uint32_t first = blockIdx.x == 0 ? 0u : first_own - kDecWarm;                // first subsequence of the span
     const int64_t isub = int64_t(first_own) - kDecWarm + t;                            // this thread's subsequence
     if (uint64_t(first_own) * p.sub_bits >= total_bits) {     // (capacity CTA beyond the data of this image)
@@ -382,8 +452,8 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
         return;
     }
     const uint64_t span_start = uint64_t(first) * p.sub_bits;                          // multiple of 128 bits
-    const uint32_t span_bits = kDecThreads * p.sub_bits;
-    load_dec_tabs(p.tabs, s_fast, s_slow);
+    const uint32_t span_bits = nthr * p.sub_bits;
+    load_dec_tabs(p.tabs, &s_tabs);
     load_span(p.ustream + img * p.uslot, span_start / 8, span_bits / 8, p.uslot, s_span);
     const uint32_t start = uint32_t(isub - int64_t(first)) * p.sub_bits, end = start + p.sub_bits;   // relative to the span
     const uint32_t limit = uint32_t(min(total_bits - span_start, uint64_t(span_bits) + 256u));
@@ -400,20 +470,20 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     bool chg = false;
     if (valid) {
         if (launch == 0) {
-            BitBuf br;
+            FastBits br;
             br.init(s_span, start);
             uint32_t b = 0, z = 0, n = 0;
-            decode_span<false>(br, b, z, n, end, limit, s_slow, s_fast, nullptr, 0, 0, nullptr, p.nb, p.ny);
+            decode_span<false>(br, b, z, n, end, limit, &s_tabs, nullptr, 0, 0, nullptr, p.nb, p.ny);
             st = pack_state(br.pos > end ? br.pos - end : 0u, b, z, n);
             chg = true;
         } else {
             st = p.sub_state[si];
             if (t == kDecWarm && blockIdx.x > 0) {
                 const uint32_t ps = tail_in[img * ncta + blockIdx.x - 1];
-                BitBuf br;
+                FastBits br;
                 br.init(s_span, start + (ps & 63u));
                 uint32_t b = (ps >> 6) & 7u, z = (ps >> 9) & 63u, n = 0;
-                decode_span<false>(br, b, z, n, end, limit, s_slow, s_fast, nullptr, 0, 0, nullptr, p.nb, p.ny);
+                decode_span<false>(br, b, z, n, end, limit, &s_tabs, nullptr, 0, 0, nullptr, p.nb, p.ny);
                 const uint32_t ns = pack_state(br.pos > end ? br.pos - end : 0u, b, z, n);
                 chg = ((ns ^ st) & kStateSyncMask) != 0;
                 st = ns;
@@ -424,16 +494,16 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     s_chg[0][t] = chg ? 1 : 0;
     uint32_t nchanged = (launch > 0 && chg) ? 1u : 0u;
     __syncthreads();
-    for (int it = 0; it < 4 * kDecThreads; ++it) {
+    for (int it = 0; it < 4 * kDecThreads; ++it) {     // (a chain cannot be longer than the CTA)
         // (the very first subsequence of the image has no predecessor: its guessed state is the true one)
         const bool redo = valid && isub > 0 && t > 0 && s_chg[it & 1][t - 1];
         const uint32_t ps = redo ? s_state[t - 1] : 0u;
         bool c2 = false;
         if (redo) {
-            BitBuf br;
+            FastBits br;
             br.init(s_span, start + (ps & 63u));
             uint32_t b = (ps >> 6) & 7u, z = (ps >> 9) & 63u, n = 0;
-            decode_span<false>(br, b, z, n, end, limit, s_slow, s_fast, nullptr, 0, 0, nullptr, p.nb, p.ny);
+            decode_span<false>(br, b, z, n, end, limit, &s_tabs, nullptr, 0, 0, nullptr, p.nb, p.ny);
             const uint32_t ns = pack_state(br.pos > end ? br.pos - end : 0u, b, z, n);
             c2 = ((ns ^ st) & kStateSyncMask) != 0;
             st = ns;
@@ -450,7 +520,7 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     const bool mine = valid && owner;
     if (mine) p.sub_state[si] = st;
     // the CTA's last valid subsequence is the seed of the next CTA
-    const bool is_tail = mine && (t == kDecThreads - 1 || end >= limit || isub + 1 >= int64_t(p.nsub));
+    const bool is_tail = mine && (t == int(nthr) - 1 || end >= limit || isub + 1 >= int64_t(p.nsub));
     if (is_tail) tail_out[img * ncta + blockIdx.x] = st;
     if (launch > 0 && nchanged) atomicAdd(p.changed + (host_poll ? 1 : launch), (unsigned long long)nchanged);
     // blocks completed inside this CTA's own subsequences (input of the block-index scan)
@@ -467,7 +537,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const DecParams p, const u
     const size_t img = blockIdx.x;
     const uint64_t total_bits = p.ubytes[img] * 8;
     const uint32_t nsub = uint32_t(min(uint64_t(p.nsub), (total_bits + p.sub_bits - 1) / p.sub_bits));
-    const uint32_t n = (nsub + kDecOwn - 1) / kDecOwn;
+    const uint32_t n = (nsub + p.cta_own - 1) / p.cta_own;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     for (uint32_t c0 = 0; c0 < n; c0 += 1024) {
@@ -497,21 +567,20 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const DecParams p, const u
 __global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p)
 {
     extern __shared__ __align__(16) uint32_t s_span[];
-    __shared__ __align__(16) uint32_t s_fast[4][1 << kLutBits];
-    __shared__ __align__(16) HuffSlow s_slow[4];
+    __shared__ __align__(16) DecTabs s_tabs;
     __shared__ uint32_t s_warp[kDecThreads / 32];
     const size_t img = blockIdx.y;
     const uint64_t total_bits = p.ubytes[img] * 8;
-    // same ownership as k_sync_decode (kDecOwn subsequences per CTA; the last kDecWarm threads idle)
-    const uint64_t cta_start = uint64_t(blockIdx.x) * kDecOwn * p.sub_bits;
+    // same ownership as k_sync_decode (p.cta_own subsequences per CTA; the last kDecWarm threads idle)
+    const uint64_t cta_start = uint64_t(blockIdx.x) * p.cta_own * p.sub_bits;
     if (cta_start >= total_bits) return;
-    const uint32_t span_bits = kDecOwn * p.sub_bits;
-    load_dec_tabs(p.tabs, s_fast, s_slow);
+    const uint32_t span_bits = p.cta_own * p.sub_bits;
+    load_dec_tabs(p.tabs, &s_tabs);
     load_span(p.ustream + img * p.uslot, cta_start / 8, span_bits / 8, p.uslot, s_span);
-    const uint32_t i = blockIdx.x * kDecOwn + threadIdx.x;
+    const uint32_t i = blockIdx.x * p.cta_own + threadIdx.x;
     const uint32_t start = threadIdx.x * p.sub_bits;
     const uint32_t limit = uint32_t(min(total_bits - cta_start, uint64_t(span_bits) + 256u));
-    const bool valid = threadIdx.x < kDecOwn && start < limit && i < p.nsub;
+    const bool valid = threadIdx.x < p.cta_own && start < limit && i < p.nsub;
     const size_t si = img * p.nsub + i;
     const uint32_t mine = valid ? p.sub_state[si] : 0u;
     __syncthreads();
@@ -524,10 +593,10 @@ __global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p)
         const uint32_t ps = p.sub_state[si - 1];
         pos = start + (ps & 63u), b = (ps >> 6) & 7u, z = (ps >> 9) & 63u;
     }
-    BitBuf br;
+    FastBits br;
     br.init(s_span, pos);
     int corrupt = 0;
-    decode_span<true>(br, b, z, n, start + p.sub_bits, limit, s_slow, s_fast, p.coefs + img * p.coef_stride, blk, p.nblk, &corrupt, p.nb, p.ny);
+    decode_span<true>(br, b, z, n, start + p.sub_bits, limit, &s_tabs, p.coefs + img * p.coef_stride, blk, p.nblk, &corrupt, p.nb, p.ny);
     if (corrupt && p.status) p.status[img] = JPEZYB200_ECORRUPT;
 }
 
@@ -536,9 +605,8 @@ __global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p)
 // resets pred_dct[]; the segments between the markers were located by the un-stuffing pass (seg_start).
 __global__ void __launch_bounds__(128) k_decode_segments(const DecParams p)
 {
-    __shared__ __align__(16) uint32_t s_fast[4][1 << kLutBits];
-    __shared__ __align__(16) HuffSlow s_slow[4];
-    load_dec_tabs(p.tabs, s_fast, s_slow);
+    __shared__ __align__(16) DecTabs s_tabs;
+    load_dec_tabs(p.tabs, &s_tabs);
     __syncthreads();
     const size_t img = blockIdx.y;
     const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
@@ -576,11 +644,12 @@ __global__ void __launch_bounds__(128) k_decode_segments(const DecParams p)
                 br.refill();
                 const uint32_t w = br.peek32();
                 const uint32_t ti = (z == 0u ? 0u : 2u) + cls;
-                uint32_t e = s_fast[ti][w >> (32 - kLutBits)];
-                if (e == 0u) e = huff_lookup_slow(s_slow + ti, w);
+                uint32_t e = s_tabs.fast[ti][w >> (32 - kLutBits)];
+                if (e == 0u) e = huff_lookup_slow(s_tabs.slow + ti, w);
                 if (e == 0u) { corrupt = 1; break; }
-                br.skip(int(e & 31u));
-                const uint32_t dz = (e >> 8) & 127u, len = (e >> 16) & 31u, sz = e >> 21;
+                const uint32_t dz = (e >> 8) & 127u, len = (e >> 16) & 31u, sz = (e >> 21) & 15u;
+                const bool fold = (e & kEntryEob) && z + dz < 64u;       // see huff_entry: the folded EOB only counts inside the block
+                br.skip(int(e & 31u) - ((e & kEntryEob) && !fold ? int((e >> 25) & 15u) : 0));
                 const uint32_t kk = z + dz - 1u;
                 if (kk > 63u && dz != 64u) { corrupt = 1; break; }
                 if (sz) {
@@ -592,7 +661,7 @@ __global__ void __launch_bounds__(128) k_decode_segments(const DecParams p)
                 } else if (z == 0u) {
                     blk[0] = int16_t(pred[comp]);
                 }
-                z += dz;
+                z = fold ? 64u : z + dz;
             }
             if (corrupt) break;
         }

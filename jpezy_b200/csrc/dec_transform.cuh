@@ -322,21 +322,15 @@ __device__ __forceinline__ void idct_block(const InvParams& p, const uint4* __re
 
 // FP64 re-evaluation of one sample of block `cz` (zig-zag int16 coefficients, non-zero only below position nlim) with
 // quantiser table qt (natural order)
-__device__ __noinline__ int idct_fix(const int16_t* __restrict__ cz, const uint16_t* __restrict__ qt, int nlim, int x, int y, uint32_t* exact_hits)
+__device__ __noinline__ int idct_fix_finish(double acc, const int16_t* __restrict__ cz, const uint16_t* __restrict__ qt, int nlim, int x, int y,
+                                            uint32_t* exact_hits)
 {
-    double acc = 0.0;
-    unsigned long long nzmask = 0;
-    for (int n = 0; n < nlim; ++n) {
-        const int c = cz[n];
-        if (!c) continue;
-        const int nat = cC.zz[n], v = nat >> 3, u = nat & 7;
-        nzmask |= 1ull << nat;
-        const double f = double(c * int(qt[nat])) * (u ? 1.0 : 0.70710678118654752440) * (v ? 1.0 : 0.70710678118654752440);
-        acc = fma(f * cC.cos_ref[u * 8 + x], cC.cos_ref[v * 8 + y], acc);
-    }
     const double val = acc * 0.25 + 128.0;
     if (fabs(val - rint(val)) >= 1e-9) return __double2int_rz(val);
     // the reference's exact operation order: natural order ascending, zero terms cannot change the sum
+    unsigned long long nzmask = 0;
+    for (int n = 0; n < nlim; ++n)
+        if (cz[n]) nzmask |= 1ull << cC.zz[n];
     double sum = 0.0;
     while (nzmask) {
         const int nat = __ffsll((long long)nzmask) - 1;
@@ -351,6 +345,25 @@ __device__ __noinline__ int idct_fix(const int16_t* __restrict__ cz, const uint1
     }
     ++*exact_hits;
     return __double2int_rz(__dadd_rn(__dmul_rn(sum, 0.25), 128.0));
+}
+
+// partial FP64 sum of sample (x, y) over the zig-zag positions first, first + step, ... below nlim
+__device__ __forceinline__ double idct_fix_part(const int16_t* __restrict__ cz, const uint16_t* __restrict__ qt, int first, int step, int nlim, int x, int y)
+{
+    double acc = 0.0;
+    for (int n = first; n < nlim; n += step) {
+        const int c = cz[n];
+        if (!c) continue;
+        const int nat = cC.zz[n], v = nat >> 3, u = nat & 7;
+        const double f = double(c * int(qt[nat])) * (u ? 1.0 : 0.70710678118654752440) * (v ? 1.0 : 0.70710678118654752440);
+        acc = fma(f * gCosRef[u * 8 + x], gCosRef[v * 8 + y], acc);
+    }
+    return acc;
+}
+
+__device__ __noinline__ int idct_fix(const int16_t* __restrict__ cz, const uint16_t* __restrict__ qt, int nlim, int x, int y, uint32_t* exact_hits)
+{
+    return idct_fix_finish(idct_fix_part(cz, qt, 0, 1, nlim, x, y), cz, qt, nlim, x, y, exact_hits);
 }
 
 // colour conversion of 4 horizontally adjacent pixels sharing 2 chroma pairs; y4: 4 int16 in two words
@@ -506,10 +519,13 @@ __global__ void __launch_bounds__(kInvThreads, 3) k_inv_transform(const __grid_c
         if (nfix) {
             const bool overflow = nfix > kFixCap;
             uint32_t exact_hits = 0;    // samples decided by the reference's exact operation order (JPEZYB200_STAT_GUARD_INV)
+            // eight lanes per queue entry; the loop bound is CTA-uniform so that every lane reaches the butterfly
             const uint32_t ntask = overflow ? kTileBlk * 8u : nfix * 8u;
-            for (uint32_t task = t; task < ntask; task += kInvThreads) {
+            for (uint32_t task0 = 0; task0 < ntask; task0 += kInvThreads) {
+                const uint32_t task = task0 + uint32_t(t);
+                const bool act = task < ntask;
                 // entry = blk << 7 | sample; kWholeBlock (overflow only) = every sample of the block
-                const uint32_t e = overflow ? (((task >> 3) << 7) | kWholeBlock) : s_fix[task >> 3];
+                const uint32_t e = !act ? 0u : (overflow ? (((task >> 3) << 7) | kWholeBlock) : uint32_t(s_fix[task >> 3]));
                 const uint32_t blk = (e >> 7) & 255u, sub = task & 7u;
                 const uint32_t mcu = blk / 6u, k = blk - mcu * 6u;
                 const int comp = k < 4u ? 0 : int(k) - 3;
@@ -524,11 +540,17 @@ __global__ void __launch_bounds__(kInvThreads, 3) k_inv_transform(const __grid_c
                     tile = reinterpret_cast<int16_t*>((k == 4u ? s_cb : s_cr) + mcu * 16);
                     stride = kICStride / 2;
                 }
-                if (e & kWholeBlock) {     // overflow path: row `sub` of the block, every sample in FP64
-                    for (int x = 0; x < 8; ++x) tile[sub * stride + x] = int16_t(idct_fix(cz, p.qt[comp], nlim, x, int(sub), &exact_hits));
-                } else if (sub == 0) {
+                if (overflow) {            // row `sub` of the block, every sample in FP64
+                    if (act)
+                        for (int x = 0; x < 8; ++x) tile[sub * stride + x] = int16_t(idct_fix(cz, p.qt[comp], nlim, x, int(sub), &exact_hits));
+                } else {                   // lane `sub` sums the zig-zag positions sub, sub + 8, ...; a 3-step butterfly adds the lanes
                     const int s = int(e & 63u);
-                    tile[(s >> 3) * stride + (s & 7)] = int16_t(idct_fix(cz, p.qt[comp], nlim, s & 7, s >> 3, &exact_hits));
+                    double part = act ? idct_fix_part(cz, p.qt[comp], int(sub), 8, nlim, s & 7, s >> 3) : 0.0;
+                    part += __shfl_xor_sync(0xffffffffu, part, 1);
+                    part += __shfl_xor_sync(0xffffffffu, part, 2);
+                    part += __shfl_xor_sync(0xffffffffu, part, 4);
+                    if (act && sub == 0)
+                        tile[(s >> 3) * stride + (s & 7)] = int16_t(idct_fix_finish(part, cz, p.qt[comp], nlim, s & 7, s >> 3, &exact_hits));
                 }
             }
             exact_hits = __reduce_add_sync(0xffffffffu, exact_hits);

@@ -408,20 +408,13 @@ __device__ __noinline__ void push_fix(uint32_t* s_nfix, uint16_t* s_fix, uint32_
     if (idx < kFixCap) s_fix[idx] = uint16_t(blk_ij);
 }
 
-// tier 2 / tier 3 of the guard: FP64 evaluation of one coefficient from the stored (value+128) samples
-__device__ __noinline__ int requant_exact(const uint8_t* __restrict__ tile, int stride, int i, int j, int q, unsigned long long* counter)
+// tier 2 decision on the FP64 sum `acc` of coefficient (i, j); tier 3 (the reference's exact operation order, same
+// arithmetic as dct_exact) when even that lands within 1e-9 of a quantiser multiple
+__device__ __noinline__ int requant_finish(double acc, const uint8_t* __restrict__ tile, int stride, int i, int j, int q, unsigned long long* counter)
 {
-    double acc = 0.0;
-    for (int y = 0; y < 8; ++y) {
-        double row = 0.0;
-#pragma unroll
-        for (int x = 0; x < 8; ++x) row = fma(double(int(tile[y * stride + x]) - 128), cC.cos_ref[j * 8 + x], row);
-        acc = fma(row, cC.cos_ref[i * 8 + y], acc);
-    }
     double v = acc * 0.25 * (i ? 1.0 : 0.70710678118654752440) * (j ? 1.0 : 0.70710678118654752440);
     const double k = rint(v / double(q));
     if (k != 0.0 && fabs(v - k * double(q)) < 1e-9) {
-        // tier 3: the reference's exact operation order (same arithmetic as dct_exact)
         double sum = 0.0;
         for (int y = 0; y < 8; ++y) {
             const double ci = cC.cos_ref[i * 8 + y];
@@ -433,6 +426,19 @@ __device__ __noinline__ int requant_exact(const uint8_t* __restrict__ tile, int 
         atomicAdd(counter, 1ull);
     }
     return __double2int_rz(v) / q;
+}
+
+// tier 2 / tier 3 of the guard: FP64 evaluation of one coefficient from the stored (value+128) samples
+__device__ __noinline__ int requant_exact(const uint8_t* __restrict__ tile, int stride, int i, int j, int q, unsigned long long* counter)
+{
+    double acc = 0.0;
+    for (int y = 0; y < 8; ++y) {
+        double row = 0.0;
+#pragma unroll
+        for (int x = 0; x < 8; ++x) row = fma(double(int(tile[y * stride + x]) - 128), cC.cos_ref[j * 8 + x], row);
+        acc = fma(row, cC.cos_ref[i * 8 + y], acc);
+    }
+    return requant_finish(acc, tile, stride, i, j, q, counter);
 }
 
 // quantisation of the 64 AAN outputs of one block; CLS selects the (compile-time) constant set
@@ -632,12 +638,35 @@ __global__ void __launch_bounds__(256, 2) k_fwd_transform(const FwdParams p)
                     reinterpret_cast<int16_t*>(&s_out[blk * kOutStride])[cC.izz[ij]] = int16_t(requant_exact(tile, stride, ij >> 3, ij & 7, q, p.guard_counter));
                 }
             } else {
-                for (uint32_t e = t; e < nfix; e += 256) {
-                    const uint32_t blk = s_fix[e] >> 6, ij = s_fix[e] & 63u;
+                // eight lanes per queue entry: lane `sub` evaluates row `sub` of the separable sum, a 3-step butterfly adds
+                // the rows (the tail of a tile is the latency of this phase, not its instruction count)
+                const uint32_t sub = uint32_t(t) & 7u;
+                for (uint32_t e0 = 0; e0 < nfix; e0 += 32) {
+                    const uint32_t e = e0 + (uint32_t(t) >> 3);
+                    const bool act = e < nfix;
+                    const uint32_t ent = act ? uint32_t(s_fix[e]) : 0u;
+                    const uint32_t blk = ent >> 6, ij = ent & 63u, i = ij >> 3, j = ij & 7u;
                     int stride;
                     const uint8_t* tile = block_samples(s_y, s_cb, s_cr, blk, stride);
-                    const int q = cC.quant[(blk % 6u) >= 4u][ij];
-                    reinterpret_cast<int16_t*>(&s_out[blk * kOutStride])[cC.izz[ij]] = int16_t(requant_exact(tile, stride, ij >> 3, ij & 7, q, p.guard_counter));
+                    const uint2 w = *reinterpret_cast<const uint2*>(tile + sub * stride);
+                    const double* cj = &gCosRef[j * 8];
+                    double row = double(int(w.x & 255u) - 128) * cj[0];
+                    row = fma(double(int((w.x >> 8) & 255u) - 128), cj[1], row);
+                    row = fma(double(int((w.x >> 16) & 255u) - 128), cj[2], row);
+                    row = fma(double(int(w.x >> 24) - 128), cj[3], row);
+                    row = fma(double(int(w.y & 255u) - 128), cj[4], row);
+                    row = fma(double(int((w.y >> 8) & 255u) - 128), cj[5], row);
+                    row = fma(double(int((w.y >> 16) & 255u) - 128), cj[6], row);
+                    row = fma(double(int(w.y >> 24) - 128), cj[7], row);
+                    double part = row * gCosRef[i * 8 + sub];
+                    part += __shfl_xor_sync(0xffffffffu, part, 1);
+                    part += __shfl_xor_sync(0xffffffffu, part, 2);
+                    part += __shfl_xor_sync(0xffffffffu, part, 4);
+                    if (act && sub == 0) {
+                        const int q = cC.quant[(blk % 6u) >= 4u][ij];
+                        reinterpret_cast<int16_t*>(&s_out[blk * kOutStride])[cC.izz[ij]] =
+                            int16_t(requant_finish(part, tile, stride, int(i), int(j), q, p.guard_counter));
+                    }
                 }
             }
             __syncthreads();
