@@ -25,25 +25,29 @@ namespace jz {
 constexpr int kDecThreads = 256;
 constexpr int kLutBits = 10;
 
-// compact canonical decoder table for one DHT table, built on the host
-// entry of the decoder tables (0 = no code of at most kLutBits bits starts here):
-//   bits 0..4   bits to consume: code length + size of the value field (+ the end-of-block code, see bit 5)
-//   bit  5      the end-of-block code of the block's AC table follows inside the kLutBits window and is consumed with
-//               this symbol: one table access instead of two for "DC difference, EOB" and "coefficient, EOB" (most
-//               blocks of photographic content).  Not valid when the symbol itself fills the block (z + dz >= 64: the
-//               bits that look like EOB then belong to the next block) -- the decoders give bits 25..28 back.
-//   bits 8..14  dz: advance of the zig-zag index; DC tables: 1; AC tables: run + 1, end-of-block: 64 (so that z + dz >= 64
-//               closes the block in both cases; ZRL = (15, 0) advances by 16 like the generic path of the reference,
-//               src/decoder/jpezy_decoder.hpp:611-622)
+// compact canonical decoder table for one DHT table, built on the host; entry layout:
+//   bits 0..4   bits to consume: code length + size of the value field (+ a folded end-of-block code); bits 5..7 are zero
+//               (the bit reader adds whole entries to its shift count and relies on that)
+//   bits 8..15  advance of the zig-zag index z.  DC tables: 1; AC tables: run + 1; end-of-block: 64, so that z + dz >= 64
+//               closes the block in both cases (ZRL = (15, 0) advances by 16 like the generic path of the reference,
+//               src/decoder/jpezy_decoder.hpp:611-622).
+//               64 + (run + 1): the end-of-block code of the block's AC table follows inside the kLutBits window and is
+//               consumed with this symbol -- one table access instead of two for "DC difference, EOB" and
+//               "coefficient, EOB" (most blocks of photographic content).  Not valid when the symbol itself fills the
+//               block (then z + dz >= 128: the bits that look like EOB belong to the next block); the decoders turn the
+//               entry back into the plain one with bits 25..28.
+//               255 (kEntryNone, consume = 0): no code of at most kLutBits bits starts here -> HuffSlow.
 //   bits 16..20 code length, bits 21..24 size (value extraction in the writing pass)
-//   bits 25..28 length of the end-of-block code folded in (bit 5)
-constexpr uint32_t kEntryEob = 32u;
+//   bits 25..28 length of the folded end-of-block code
+constexpr uint32_t kEntryNone = 255u << 8;
 __host__ __device__ inline uint32_t huff_entry(uint32_t len, uint32_t sym, bool ac)
 {
     const uint32_t size = sym & 15u, run = sym >> 4;
     const uint32_t dz = !ac ? 1u : (sym == 0u ? 64u : run + 1u);
     return (len + size) | (dz << 8) | (len << 16) | (size << 21);
 }
+// the plain entry of a folded one
+__host__ __device__ inline uint32_t unfold_entry(uint32_t e) { return e - ((e >> 25) & 15u) - (64u << 8); }
 struct HuffSlow {                  // codes longer than kLutBits
     int32_t maxcode[18];           // maxcode[len] (left-aligned compare uses plain codes), -1 = none
     int32_t valptr[17];            // index into vals of the first code of this length minus its code
@@ -104,7 +108,10 @@ struct DecParams {
     int16_t* coefs;           // [nimg][nblk*64]
     size_t coef_stride;
     int32_t* status;          // [nimg] or nullptr
-    // DC scan scratch
+    // DC scan: the differences are written to a dense array (2 bytes per block) instead of coefficient 0 of every block,
+    // so that the prefix sums read 12 contiguous bytes per MCU and not one 32-byte sector per block
+    int16_t* dcd;             // [nimg][nblk] DC differences, then (k_dc_apply, in place) the DC coefficients
+    uint32_t dc_dense;        // != 0: the DC coefficients stay in dcd only (the inverse transform reads them from there)
     int32_t* dc_part;         // [nimg][ndc_tiles][3]
     uint32_t ndc_tiles;
 };
@@ -161,97 +168,101 @@ __device__ __noinline__ uint32_t huff_lookup_slow(const HuffSlow* __restrict__ t
 }
 
 // ---- the reader of the synchronisation / writing passes ------------------------------------------------------
-// Same span, but the words are staged byte-swapped (big-endian bit order in every word), and 96 bits are buffered in
-// registers: with 64 <= n <= 96 before a symbol is consumed and at most 31 bits per symbol, the top word is
-// completely valid after the shift whether or not a refill follows.  The table index of the NEXT symbol therefore
-// hangs off one funnel shift of `hi`, and the refill (mid / lo / nxt only) stays off the dependent chain
-// symbol -> length -> shift -> index -> table word, which is what bounds a thread's decode rate.
+// A thread's decode rate is set by the number of instructions per symbol (one warp per scheduler issues them in order,
+// ~4 cycles apart when they depend on each other), so the loop below is written to need few:
+//  * the span is staged as byte-swapped words; two of them (hi, lo) are the bit window, a third is pre-loaded; the
+//    shift count is a running sum of whole table entries (the funnel shift looks at its low 5 bits only, bit 5 flipping
+//    says "one word used up"), the exact position is kept on the side for the loop bound;
+//  * shared memory is addressed with 32-bit shared-space addresses (no generic-address arithmetic in the loop);
+//  * the next symbol comes from the AC table of the block's class or, if this symbol closes the block, from the DC table
+//    of the next block's class: both words are fetched as soon as the window is known, the block-end test selects.
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
 struct FastBits {
-    const uint32_t* base;   // the span
-    const uint32_t* w;      // next word to pre-load (shared memory, byte-swapped words)
-    uint32_t hi, mid, lo, nxt;
-    int n;               // valid bits in hi:mid:lo
-    uint32_t pos;        // bit position of the first bit of hi, relative to the span
-    __device__ __forceinline__ void init(const uint32_t* span, uint32_t p)
+    uint32_t wa;         // shared address of the word after nx
+    uint32_t hi, lo, nx; // window words i, i + 1 and the pre-loaded word i + 2
+    uint32_t acc;        // low 5 bits: bits of hi already consumed; bit 5 flips when a word is used up; rest: junk
+    uint32_t pk;         // the next 32 bits
+    uint32_t pos;        // bit position of pk, relative to the span
+    __device__ __forceinline__ void init(uint32_t span_saddr, uint32_t p)
     {
-        base = span;
-        w = span + (p >> 5);
-        const uint32_t a = w[0], b = w[1], c = w[2];
-        nxt = w[3];
-        w += 4;
-        const uint32_t sh = p & 31u;
-        hi = __funnelshift_l(b, a, sh), mid = __funnelshift_l(c, b, sh), lo = c << sh;
-        n = 96 - int(sh);
+        const uint32_t a = span_saddr + ((p >> 5) << 2);
+        hi = lds32(a), lo = lds32(a + 4), nx = lds32(a + 8);
+        wa = a + 12;
+        acc = p & 31u;
+        pk = __funnelshift_l(lo, hi, acc);
         pos = p;
     }
-    // drop k <= 31 bits (only the low 5 bits of k are looked at) and top the buffer up; `hi` is final after the first line
-    __device__ __forceinline__ void consume(uint32_t k)
+    // drop the bits of table entry e (<= 31, bits 5..7 of e are zero)
+    __device__ __forceinline__ void consume(uint32_t e)
     {
-        hi = __funnelshift_l(mid, hi, k);
-        mid = __funnelshift_l(lo, mid, k);
-        lo <<= (k & 31u);
-        n -= int(k & 31u);
-        pos += k & 31u;
-        const bool rf = n < 64;                       // then lo is empty and 33 <= n: append nxt behind bit n
-        const uint32_t s = uint32_t(n) & 31u;         // n - 32 for 33..63
-        const uint32_t add_mid = s ? nxt >> s : 0u;   // (n == 32 cannot happen with k <= 31; s == 0 only at n == 64)
-        mid |= rf ? add_mid : 0u;
-        lo = rf ? nxt << ((32u - s) & 31u) : lo;
-        if (rf) nxt = *w++;
-        n += rf ? 32 : 0;
+        const uint32_t a2 = acc + e;
+        if ((a2 ^ acc) & 32u) {
+            hi = lo, lo = nx;
+            nx = lds32(wa);
+            wa += 4;
+        }
+        acc = a2;
+        pk = __funnelshift_l(lo, hi, a2);
+        pos += e & 31u;
     }
 };
 
 // Decode from (br.pos, b, z) until br.pos >= end (or >= limit); positions are relative to the span.  With kWrite the
 // coefficients that carry a value field are stored (the buffer is pre-zeroed), block ordinals start at blk.
-// s_fast: [0] = DC class 0 (luma), [1] = DC class 1, [2] = AC class 0, [3] = AC class 1 (contiguous).
-// The next symbol comes from the AC table of the block's class, or, if this symbol closes the block, from the DC table
-// of the next block's class: both words are fetched as soon as the index is known and the block-end test selects.
+// Tables: T->fast[0] = DC class 0 (luma), [1] = DC class 1, [2] = AC class 0, [3] = AC class 1 (contiguous).
 template <bool kWrite>
 __device__ __forceinline__ void decode_span(FastBits& br, uint32_t& b, uint32_t& z, uint32_t& nblocks, const uint32_t end,
-                                            const uint32_t limit, const DecTabs* __restrict__ T, int16_t* __restrict__ out, uint64_t blk,
-                                            const uint64_t nblk, int* corrupt, const uint32_t nb, const uint32_t ny)
+                                            const uint32_t limit, const DecTabs* __restrict__ T, int16_t* __restrict__ out,
+                                            int16_t* __restrict__ dcd, uint64_t blk, const uint64_t nblk, int* corrupt,
+                                            const uint32_t nb, const uint32_t ny)
 {
     const uint32_t stop = end < limit ? end : limit;
-    const uint32_t* tab = &T->fast[0][0];
+    uint32_t tab;              // (opaque to the compiler, which would otherwise re-derive the shared-window address per symbol)
+    asm volatile("mov.u32 %0, %1;" : "=r"(tab) : "r"(uint32_t(__cvta_generic_to_shared(&T->fast[0][0]))));
     uint32_t bn = (b + 1u == nb) ? 0u : b + 1u;                       // the block after this one
     uint32_t t_cont = (2u + (b >= ny ? 1u : 0u)) << kLutBits;         // AC table of this block
     uint32_t t_new = (bn >= ny ? 1u : 0u) << kLutBits;                // DC table of the next block
-    uint32_t e = tab[(z == 0u ? ((b >= ny ? 1u : 0u) << kLutBits) : t_cont) + (br.hi >> (32 - kLutBits))];
+    uint32_t e = lds32(tab + (((z == 0u ? t_cont - (2u << kLutBits) : t_cont) + (br.pk >> (32 - kLutBits))) << 2));
     while (br.pos < stop) {
-        if (e == 0u) {             // code longer than kLutBits, or none
-            const uint32_t ti = (z == 0u ? 0u : 2u) + (b >= ny ? 1u : 0u);
-            e = huff_lookup_slow(T->slow + ti, br.hi);
-            if (e == 0u) {         // no such code: only legal while speculating
-                if (kWrite && corrupt) *corrupt = 1;
-                br.consume(1);
-                e = tab[(ti << kLutBits) + (br.hi >> (32 - kLutBits))];
-                continue;
+        uint32_t dz = __byte_perm(e, 0, 0x4441);
+        if (z + dz >= 128u) {      // not a plain symbol
+            if (dz == 255u) {      // code longer than kLutBits, or none
+                const uint32_t t_cur = z == 0u ? t_cont - (2u << kLutBits) : t_cont;
+                e = huff_lookup_slow(T->slow + (t_cur >> kLutBits), br.pk);
+                if (e == 0u) {     // no such code: only legal while speculating
+                    if (kWrite && corrupt) *corrupt = 1;
+                    br.consume(1);
+                    e = lds32(tab + ((t_cur + (br.pk >> (32 - kLutBits))) << 2));
+                    continue;
+                }
+            } else {               // the symbol fills the block itself: the bits that look like EOB are the next block's
+                e = unfold_entry(e);
             }
+            dz = __byte_perm(e, 0, 0x4441);
         }
-        const uint32_t w = br.hi;
-        br.consume(e);             // code + value field (+ folded EOB) <= 31 bits
-        uint32_t idx = br.hi >> (32 - kLutBits);
-        uint32_t ea = tab[t_cont + idx], eb = tab[t_new + idx];
-        const uint32_t dz = (e >> 8) & 127u;
-        if ((e & kEntryEob) && z + dz >= 64u) {                // the symbol filled the block: the "EOB" bits are the next block's
-            br.init(br.base, br.pos - ((e >> 25) & 15u));
-            idx = br.hi >> (32 - kLutBits);
-            ea = tab[t_cont + idx], eb = tab[t_new + idx];
-        }
+        const uint32_t w = br.pk;
+        br.consume(e);
+        const uint32_t idx = br.pk >> (32 - kLutBits);
+        const uint32_t ea = lds32(tab + ((t_cont + idx) << 2)), eb = lds32(tab + ((t_new + idx) << 2));
         if (kWrite) {
             const uint32_t len = (e >> 16) & 31u, sz = (e >> 21) & 15u;
-            const uint32_t k = z + dz - 1u;                    // zig-zag index of this coefficient
+            const uint32_t k = z + ((dz - 1u) & 63u);          // zig-zag index of this coefficient
             if (k > 63u && dz != 64u) {                        // run past the end of the block (src/decoder/jpezy_decoder.hpp:619)
                 if (corrupt) *corrupt = 1;
             } else if (sz && blk < nblk) {
                 const uint32_t vbits = (w << len) >> (32 - sz);
                 int v = int(vbits);
                 if (!(vbits & (1u << (sz - 1)))) v -= (1 << sz) - 1;
-                out[blk * 64 + k] = int16_t(v);
+                if (z == 0u) dcd[blk] = int16_t(v);                // DC difference: dense side array (k_dc_sum / k_dc_apply)
+                else out[blk * 64 + k] = int16_t(v);
             }
         }
-        const bool endb = z + dz >= 64u || (e & kEntryEob);
+        const bool endb = z + dz >= 64u;
         z = endb ? 0u : z + dz;
         e = endb ? eb : ea;
         b = endb ? bn : b;
@@ -267,8 +278,20 @@ __device__ __forceinline__ void decode_span(FastBits& br, uint32_t& b, uint32_t&
 __device__ __forceinline__ void load_dec_tabs(const HuffDecTab* __restrict__ tabs, DecTabs* __restrict__ T)
 {
     constexpr int kFast16 = (1 << kLutBits) * 4 / 16, kSlowW = int(sizeof(HuffSlow) / 4);
-    for (int i = threadIdx.x; i < 4 * kFast16; i += blockDim.x)
-        reinterpret_cast<uint4*>(T->fast[i / kFast16])[i % kFast16] = __ldg(reinterpret_cast<const uint4*>(tabs[i / kFast16].fast) + i % kFast16);
+    // eight loads in flight per thread: the tables come out of L2 at its latency, not at eight times that
+    for (int i0 = threadIdx.x; i0 < 4 * kFast16; i0 += 8 * blockDim.x) {
+        uint4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = i0 + k * int(blockDim.x);
+            if (i < 4 * kFast16) v[k] = __ldg(reinterpret_cast<const uint4*>(tabs[i / kFast16].fast) + i % kFast16);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = i0 + k * int(blockDim.x);
+            if (i < 4 * kFast16) reinterpret_cast<uint4*>(T->fast[i / kFast16])[i % kFast16] = v[k];
+        }
+    }
     for (int i = threadIdx.x; i < 4 * kSlowW; i += blockDim.x)
         reinterpret_cast<uint32_t*>(&T->slow[i / kSlowW])[i % kSlowW] = __ldg(reinterpret_cast<const uint32_t*>(&tabs[i / kSlowW].slow) + i % kSlowW);
 }
@@ -455,6 +478,7 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     const uint32_t span_bits = nthr * p.sub_bits;
     load_dec_tabs(p.tabs, &s_tabs);
     load_span(p.ustream + img * p.uslot, span_start / 8, span_bits / 8, p.uslot, s_span);
+    const uint32_t span_sa = uint32_t(__cvta_generic_to_shared(s_span));
     const uint32_t start = uint32_t(isub - int64_t(first)) * p.sub_bits, end = start + p.sub_bits;   // relative to the span
     const uint32_t limit = uint32_t(min(total_bits - span_start, uint64_t(span_bits) + 256u));
     const bool owner = t >= kDecWarm;
@@ -471,9 +495,9 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     if (valid) {
         if (launch == 0) {
             FastBits br;
-            br.init(s_span, start);
+            br.init(span_sa, start);
             uint32_t b = 0, z = 0, n = 0;
-            decode_span<false>(br, b, z, n, end, limit, &s_tabs, nullptr, 0, 0, nullptr, p.nb, p.ny);
+            decode_span<false>(br, b, z, n, end, limit, &s_tabs, nullptr, nullptr, 0, 0, nullptr, p.nb, p.ny);
             st = pack_state(br.pos > end ? br.pos - end : 0u, b, z, n);
             chg = true;
         } else {
@@ -481,9 +505,9 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
             if (t == kDecWarm && blockIdx.x > 0) {
                 const uint32_t ps = tail_in[img * ncta + blockIdx.x - 1];
                 FastBits br;
-                br.init(s_span, start + (ps & 63u));
+                br.init(span_sa, start + (ps & 63u));
                 uint32_t b = (ps >> 6) & 7u, z = (ps >> 9) & 63u, n = 0;
-                decode_span<false>(br, b, z, n, end, limit, &s_tabs, nullptr, 0, 0, nullptr, p.nb, p.ny);
+                decode_span<false>(br, b, z, n, end, limit, &s_tabs, nullptr, nullptr, 0, 0, nullptr, p.nb, p.ny);
                 const uint32_t ns = pack_state(br.pos > end ? br.pos - end : 0u, b, z, n);
                 chg = ((ns ^ st) & kStateSyncMask) != 0;
                 st = ns;
@@ -501,9 +525,9 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
         bool c2 = false;
         if (redo) {
             FastBits br;
-            br.init(s_span, start + (ps & 63u));
+            br.init(span_sa, start + (ps & 63u));
             uint32_t b = (ps >> 6) & 7u, z = (ps >> 9) & 63u, n = 0;
-            decode_span<false>(br, b, z, n, end, limit, &s_tabs, nullptr, 0, 0, nullptr, p.nb, p.ny);
+            decode_span<false>(br, b, z, n, end, limit, &s_tabs, nullptr, nullptr, 0, 0, nullptr, p.nb, p.ny);
             const uint32_t ns = pack_state(br.pos > end ? br.pos - end : 0u, b, z, n);
             c2 = ((ns ^ st) & kStateSyncMask) != 0;
             st = ns;
@@ -577,6 +601,7 @@ __global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p)
     const uint32_t span_bits = p.cta_own * p.sub_bits;
     load_dec_tabs(p.tabs, &s_tabs);
     load_span(p.ustream + img * p.uslot, cta_start / 8, span_bits / 8, p.uslot, s_span);
+    const uint32_t span_sa = uint32_t(__cvta_generic_to_shared(s_span));
     const uint32_t i = blockIdx.x * p.cta_own + threadIdx.x;
     const uint32_t start = threadIdx.x * p.sub_bits;
     const uint32_t limit = uint32_t(min(total_bits - cta_start, uint64_t(span_bits) + 256u));
@@ -594,9 +619,9 @@ __global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p)
         pos = start + (ps & 63u), b = (ps >> 6) & 7u, z = (ps >> 9) & 63u;
     }
     FastBits br;
-    br.init(s_span, pos);
+    br.init(span_sa, pos);
     int corrupt = 0;
-    decode_span<true>(br, b, z, n, start + p.sub_bits, limit, &s_tabs, p.coefs + img * p.coef_stride, blk, p.nblk, &corrupt, p.nb, p.ny);
+    decode_span<true>(br, b, z, n, start + p.sub_bits, limit, &s_tabs, p.coefs + img * p.coef_stride, p.dcd + img * p.nblk, blk, p.nblk, &corrupt, p.nb, p.ny);
     if (corrupt && p.status) p.status[img] = JPEZYB200_ECORRUPT;
 }
 
@@ -645,11 +670,13 @@ __global__ void __launch_bounds__(128) k_decode_segments(const DecParams p)
                 const uint32_t w = br.peek32();
                 const uint32_t ti = (z == 0u ? 0u : 2u) + cls;
                 uint32_t e = s_tabs.fast[ti][w >> (32 - kLutBits)];
-                if (e == 0u) e = huff_lookup_slow(s_tabs.slow + ti, w);
+                if (e == kEntryNone) e = huff_lookup_slow(s_tabs.slow + ti, w);
                 if (e == 0u) { corrupt = 1; break; }
-                const uint32_t dz = (e >> 8) & 127u, len = (e >> 16) & 31u, sz = (e >> 21) & 15u;
-                const bool fold = (e & kEntryEob) && z + dz < 64u;       // see huff_entry: the folded EOB only counts inside the block
-                br.skip(int(e & 31u) - ((e & kEntryEob) && !fold ? int((e >> 25) & 15u) : 0));
+                if (((e >> 8) & 255u) > 64u && z + ((e >> 8) & 255u) >= 128u) e = unfold_entry(e);   // see huff_entry
+                br.skip(int(e & 31u));
+                const uint32_t dzf = (e >> 8) & 255u, len = (e >> 16) & 31u, sz = (e >> 21) & 15u;
+                const bool fold = dzf > 64u;
+                const uint32_t dz = fold ? dzf - 64u : dzf;
                 const uint32_t kk = z + dz - 1u;
                 if (kk > 63u && dz != 64u) { corrupt = 1; break; }
                 if (sz) {
@@ -678,9 +705,9 @@ __global__ void __launch_bounds__(256) k_dc_sum(const DecParams p)
     const uint32_t m = blockIdx.x * 256 + threadIdx.x;
     int y = 0, cb = 0, cr = 0;
     if (m < p.nmcu) {
-        const int16_t* c = p.coefs + img * p.coef_stride + size_t(m) * p.nb * 64;
-        for (uint32_t k = 0; k < p.ny; ++k) y += int(c[k * 64]);
-        if (p.nb > p.ny) cb = c[p.ny * 64], cr = c[(p.ny + 1) * 64];
+        const int16_t* c = p.dcd + img * p.nblk + size_t(m) * p.nb;
+        for (uint32_t k = 0; k < p.ny; ++k) y += int(c[k]);
+        if (p.nb > p.ny) cb = c[p.ny], cr = c[p.ny + 1];
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -722,10 +749,12 @@ __global__ void __launch_bounds__(256) k_dc_apply(const DecParams p)
     __shared__ int s_w[3][8];
     const size_t img = blockIdx.y;
     const uint32_t m = blockIdx.x * 256 + threadIdx.x;
-    int16_t* c = p.coefs + img * p.coef_stride + size_t(min(m, p.nmcu - 1)) * p.nb * 64;
+    const size_t mc = min(m, p.nmcu - 1);
+    int16_t* dd = p.dcd + img * p.nblk + mc * p.nb;
+    int16_t* c = p.coefs + img * p.coef_stride + mc * p.nb * 64;
     int d[6] = {0, 0, 0, 0, 0, 0};
     if (m < p.nmcu) {
-        for (uint32_t k = 0; k < p.nb; ++k) d[k] = c[k * 64];
+        for (uint32_t k = 0; k < p.nb; ++k) d[k] = dd[k];
     }
     int v[3] = {0, 0, 0};
     for (uint32_t k = 0; k < p.ny; ++k) v[0] += d[k];
@@ -754,11 +783,12 @@ __global__ void __launch_bounds__(256) k_dc_apply(const DecParams p)
     int py = incl[0] - v[0];   // predictor before this MCU
     for (uint32_t k = 0; k < p.ny; ++k) {
         py += d[k];
-        c[k * 64] = int16_t(py);
+        d[k] = py;
     }
-    if (p.nb > p.ny) {
-        c[p.ny * 64] = int16_t(incl[1]);
-        c[(p.ny + 1) * 64] = int16_t(incl[2]);
+    if (p.nb > p.ny) d[p.ny] = incl[1], d[p.ny + 1] = incl[2];
+    for (uint32_t k = 0; k < p.nb; ++k) {
+        dd[k] = int16_t(d[k]);
+        if (!p.dc_dense) c[k * 64] = int16_t(d[k]);
     }
 }
 

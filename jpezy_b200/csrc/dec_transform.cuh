@@ -23,6 +23,7 @@ namespace jz {
 
 struct InvParams {
     const int16_t* coefs;
+    const int16_t* dc;        // != nullptr: [nimg][nblk] DC coefficients kept apart from `coefs` (whose position 0 is then 0)
     size_t coef_stride;
     uint8_t *r, *g, *b;
     size_t plane_stride;      // bytes between images (= plane_bytes)
@@ -425,6 +426,13 @@ __global__ void __launch_bounds__(kInvThreads, 3) k_inv_transform(const __grid_c
     const size_t img = blockIdx.z;
     const uint32_t nvalid = min(uint32_t(kTileMcu), p.HU - mx0);
     if (t == 0) *s_nfix = 0;
+    // the block this thread transforms in phase 1 (warps 0..3 luma, 4 Cb, 5 Cr); luma: warp 0 = top blocks of MCUs 0..15,
+    // warp 1 = their bottom blocks, warps 2/3 = MCUs 16..31
+    const uint32_t my_blk = warp < 4 ? ((warp >> 1) * 16 + (lane >> 1)) * 6 + (warp & 1) * 2 + (lane & 1) : uint32_t(lane) * 6 + warp;
+    // its DC coefficient when the entropy decoder kept those in the dense side array (DecParams::dcd): position 0 of the
+    // block is 0 in `coefs` then; fetched now, merged in phase 1
+    uint32_t my_dc = 0;
+    if (p.dc && my_blk < nvalid * 6u) my_dc = uint16_t(__ldg(p.dc + img * (p.coef_stride >> 6) + (size_t(my) * p.HU + mx0) * 6 + my_blk));
 
     // ---- phase 0: coalesced load of the tile's coefficients into the padded staging buffer ----
     {
@@ -459,7 +467,11 @@ __global__ void __launch_bounds__(kInvThreads, 3) k_inv_transform(const __grid_c
         const uint32_t mask = s_mask[blk];
         const uint32_t wm = __reduce_or_sync(0xffffffffu, mask);
         const uint4* src = reinterpret_cast<const uint4*>(&s_coef[blk * kOutStride]);
-        const uint4 raw0 = src[0];
+        uint4 raw0 = src[0];
+        if (p.dc) {                // (the fix-up phase reads the block from shared memory again)
+            raw0.x |= my_dc;
+            *reinterpret_cast<uint32_t*>(&s_coef[blk * kOutStride]) = raw0.x;
+        }
         const bool dc_only = mask <= 1u && ((raw0.x >> 16) | raw0.y | raw0.z | raw0.w) == 0u;
         if (__all_sync(0xffffffffu, dc_only)) {
             // every block of the warp is DC-only: ((c*c)*F)*1*1, /4, +128 exactly as the reference evaluates it
