@@ -124,6 +124,19 @@ int jpezyb200_ctx_create(int device, jpezyb200_ctx** out)
                         qc.T[c][i * 8 + j] = float((1.0 - 2.0 * Gd) / K);
                     }
             JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(cQ, &qc, sizeof qc));
+            QuantCol col[2][8];
+            uint2 izzc[8];
+            for (int j = 0; j < 8; ++j) {
+                uint8_t zb[8];
+                for (int i = 0; i < 8; ++i) {
+                    for (int c = 0; c < 2; ++c) col[c][j].K[i] = qc.K[c][i * 8 + j], col[c][j].T[i] = qc.T[c][i * 8 + j], col[c][j].G[i] = qc.G[c][i * 8 + j];
+                    zb[i] = h.izz[i * 8 + j];
+                }
+                izzc[j].x = uint32_t(zb[0]) | (uint32_t(zb[1]) << 8) | (uint32_t(zb[2]) << 16) | (uint32_t(zb[3]) << 24);
+                izzc[j].y = uint32_t(zb[4]) | (uint32_t(zb[5]) << 8) | (uint32_t(zb[6]) << 16) | (uint32_t(zb[7]) << 24);
+            }
+            JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(gQcol, col, sizeof col));
+            JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(gIzzCol, izzc, sizeof izzc));
         }
         HuffEncLut lut[2];
         build_enc_lut(kDcLuma, kAcLuma, &lut[0]);
@@ -279,7 +292,14 @@ static int launch_fwd(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g
         k_fwd_transform_f64<<<grid, kFwdThreads, 0, st>>>(p);
     } else {
         dim3 grid((p.HU + kTileMcu - 1) / kTileMcu, p.VU, nimg);
-        k_fwd_transform<<<grid, 256, 0, st>>>(p);
+        if (ctx->transform_variant == 2) k_fwd_transform_t<false><<<grid, 256, 0, st>>>(p);    // one thread per block (A/B runs)
+        else {
+            if (!ctx->fwd_attr_set) {   // static + dynamic shared memory exceed 48 KiB: opt in once per context
+                JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdTrSmem));
+                ctx->fwd_attr_set = true;
+            }
+            k_fwd_transform_t<true><<<grid, 256, kFwdTrSmem, st>>>(p);
+        }
     }
     ++ctx->launches;
     JZ_CUDA_TRY(ctx, cudaGetLastError());

@@ -211,6 +211,7 @@ constexpr int kTileBlk = kTileMcu * 6;
 constexpr int kYStride = 528;      // bytes per row of the luma tile (512 + 16: keeps 16-byte alignment)
 constexpr int kCStride = 272;      // bytes per row of a chroma tile (256 + 16)
 constexpr int kOutStride = 144;    // bytes per block in the staging buffer (128 + 16)
+constexpr int kFwdTrSmem = 8 * 4 * 72 * 4;   // dynamic shared memory of k_fwd_transform_t<true>: the transpose scratch
 
 struct QuantConst {
     float K[2][64];   // 1 / (8 * aan_i * aan_j * q_ij)
@@ -218,6 +219,15 @@ struct QuantConst {
     float G[2][64];   // guard band in w units
 };
 static __constant__ QuantConst cQ;
+// the same constants per (class, column j), for the eight-lanes-per-block DCT whose lanes hold one column each (a
+// constant-bank load with a lane-dependent index would serialise): K and G of coefficients (i, j), i = 0..7
+struct QuantCol {
+    float K[8];
+    float T[8];
+    float G[8];
+};
+static __device__ QuantCol gQcol[2][8];
+static __device__ uint2 gIzzCol[8];     // zig-zag positions of coefficients (0..7, j), one byte each
 
 // worst-case first-order FP32 error of the AAN flowgraph in v units (tools/aan_error_bound.py), rounded up
 static const float kAanErrBound[64] = {
@@ -496,8 +506,13 @@ __device__ __forceinline__ const uint8_t* block_samples(const uint8_t* s_y, cons
     return (k == 4u ? s_cb : s_cr) + mcu * 8;
 }
 
-__global__ void __launch_bounds__(256, 2) k_fwd_transform(const FwdParams p)
+// V8 = true: phase 2 with eight lanes per block (one row, then one column each; the 8x8 transpose goes through a
+// per-warp scratch in shared memory).  A thread then carries 8 samples instead of 64: half the registers, twice the
+// resident warps -- the kernel is latency bound (ncu: issue slots 42 % busy at 16 warps per SM), not throughput bound.
+template <bool V8>
+__global__ void __launch_bounds__(256, V8 ? 4 : 2) k_fwd_transform_t(const FwdParams p)
 {
+    extern __shared__ __align__(16) float s_tr[];                 // V8: [warp][block of the pass][8 rows x 8 + 8 pad] (kFwdTrSmem)
     __shared__ __align__(16) uint8_t s_y[16 * kYStride];
     __shared__ __align__(16) uint8_t s_cb[8 * kCStride];
     __shared__ __align__(16) uint8_t s_cr[8 * kCStride];
@@ -572,6 +587,83 @@ __global__ void __launch_bounds__(256, 2) k_fwd_transform(const FwdParams p)
     }
     __syncthreads();
 
+    if constexpr (V8) {
+        // ---- phase 2: DCT + quantisation, eight lanes per block, four blocks per warp and pass ----
+        // passes 0..3: the 128 luma blocks (luma block lb = pass * 32 + warp * 4 + g: MCU lb >> 2, block lb & 3);
+        // passes 4..5: the 32 Cb and the 32 Cr blocks
+        const int g = lane >> 3, j = lane & 7;
+        float* scr = &s_tr[(warp * 4 + g) * 72];
+        const uint2 izz = gIzzCol[j];
+#pragma unroll
+        for (int cls = 0; cls < 2; ++cls) {
+            float K[8], T[8];
+            {
+                const float4* q4 = reinterpret_cast<const float4*>(&gQcol[cls][j]);
+                const float4 k0 = q4[0], k1 = q4[1], t0 = q4[2], t1 = q4[3];
+                K[0] = k0.x, K[1] = k0.y, K[2] = k0.z, K[3] = k0.w, K[4] = k1.x, K[5] = k1.y, K[6] = k1.z, K[7] = k1.w;
+                T[0] = t0.x, T[1] = t0.y, T[2] = t0.z, T[3] = t0.w, T[4] = t1.x, T[5] = t1.y, T[6] = t1.z, T[7] = t1.w;
+                if (j == 0) T[0] = 3.0e38f;        // the DC coefficient takes its own path
+            }
+#pragma unroll 1
+            for (int pass = 0; pass < (cls ? 2 : 4); ++pass) {
+                const uint32_t n = uint32_t(pass) * 32u + uint32_t(warp) * 4u + uint32_t(g);
+                uint32_t blk;
+                const uint8_t* row;
+                if (cls == 0) {
+                    const uint32_t mcu = n >> 2, k = n & 3u;
+                    blk = mcu * 6u + k;
+                    row = &s_y[((k >> 1) * 8 + j) * kYStride + mcu * 16 + (k & 1u) * 8];
+                } else {
+                    const uint32_t mcu = n & 31u, comp = n >> 5;
+                    blk = mcu * 6u + 4u + comp;
+                    row = (comp ? s_cr : s_cb) + j * kCStride + mcu * 8;
+                }
+                float d[8];
+                {
+                    const uint2 w = *reinterpret_cast<const uint2*>(row);
+                    d[0] = float(w.x & 255u), d[1] = float((w.x >> 8) & 255u), d[2] = float((w.x >> 16) & 255u), d[3] = float(w.x >> 24);
+                    d[4] = float(w.y & 255u), d[5] = float((w.y >> 8) & 255u), d[6] = float((w.y >> 16) & 255u), d[7] = float(w.y >> 24);
+                }
+                aan_fdct8(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);      // row j of the block
+                *reinterpret_cast<float4*>(&scr[j * 8]) = make_float4(d[0], d[1], d[2], d[3]);
+                *reinterpret_cast<float4*>(&scr[j * 8 + 4]) = make_float4(d[4], d[5], d[6], d[7]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] = scr[i * 8 + j];
+                __syncwarp();
+                aan_fdct8(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);      // column j: d[i] = coefficient (i, j)
+                int16_t* out = reinterpret_cast<int16_t*>(&s_out[blk * kOutStride]);
+                // rows of coefficients in which some lane of the warp may quantise to a non-zero value (|y| >= T <=> |w| >= 1 - 2G)
+                uint32_t lm = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) lm |= (fabsf(d[i]) >= T[i] ? 1u : 0u) << i;
+                const uint32_t wm = __reduce_or_sync(0xffffffffu, lm);
+                int qv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    qv[i] = 0;
+                    if (wm & (1u << i)) {
+                        const float w = d[i] * K[i];
+                        qv[i] = __float2int_rz(w);
+                        // distance of |w| to the nearest integer >= 1
+                        const float a = fabsf(w) - 0.5f;
+                        const float kf = (a + 12582912.0f) - 12582912.0f;      // rint(|w| - 0.5)
+                        const float delta = a - kf;                             // frac(|w|) - 0.5 in [-0.5, 0.5]
+                        if (fabsf(delta) > 0.5f - gQcol[cls][j].G[i] && fabsf(w) > 0.5f && (i | j) != 0)
+                            push_fix(&s_nfix, s_fix, (blk << 6) | uint32_t(i * 8 + j));
+                    }
+                }
+                if (j == 0) {
+                    // DC: the reference's sum is an exact integer (cos row 0 is 1.0), so its value is ((S*c)*c)/4 exactly as
+                    // evaluated; level shift: the samples are stored as value + 128 (64 * 128, exact)
+                    const double v = __dmul_rn(__dmul_rn(__dmul_rn(double(d[0] - 8192.0f), cC.inv_sqrt2_ref), cC.inv_sqrt2_ref), 0.25);
+                    qv[0] = cls ? __double2int_rz(v) / 17 : __double2int_rz(v) / 16;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) out[__byte_perm(i < 4 ? izz.x : izz.y, 0, 0x4440 + (i & 3))] = int16_t(qv[i]);
+            }
+        }
+    } else
     // ---- phase 2: DCT + quantisation, one thread per block (warps 0..3 luma, 4 Cb, 5 Cr) ----
     if (warp < 6) {
         // luma: warp 0 = top blocks of MCUs 0..15, warp 1 = bottom blocks of MCUs 0..15, warps 2/3 = MCUs 16..31,
