@@ -167,7 +167,7 @@ void jpezyb200_ctx_destroy(jpezyb200_ctx* ctx)
     jz_devbuf* bufs[] = {&ctx->coefs, &ctx->blk_off, &ctx->tile_sum, &ctx->tile_base, &ctx->img_bits, &ctx->ustream,
                          &ctx->ff_sum, &ctx->ff_base, &ctx->planes_in, &ctx->planes_out, &ctx->scan_io, &ctx->sizes_io,
                          &ctx->dec_scanbytes, &ctx->dec_chunk_cnt, &ctx->dec_chunk_base, &ctx->dec_ubytes, &ctx->dec_state,
-                         &ctx->dec_dirty, &ctx->dec_subblk, &ctx->dec_dc, &ctx->dec_dcd, &ctx->dec_status, &ctx->dec_changed, &ctx->shard_geom, &ctx->dec_mcnt, &ctx->dec_mbase, &ctx->dec_seg};
+                         &ctx->dec_dirty, &ctx->dec_subblk, &ctx->dec_dc, &ctx->dec_dcd, &ctx->blk_meta, &ctx->dec_status, &ctx->dec_changed, &ctx->shard_geom, &ctx->dec_mcnt, &ctx->dec_mbase, &ctx->dec_seg};
     for (jz_devbuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_enc_lut) cudaFree(ctx->d_enc_lut);
@@ -274,7 +274,8 @@ static int check_geometry(jpezyb200_ctx* ctx, uint32_t W, uint32_t H, uint32_t n
 
 // rows: MCU rows [row0, row0 + nrows) only (nrows == 0: all); the planes always hold the whole image
 static int launch_fwd(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g, const uint8_t* d_b, uint32_t W, uint32_t H,
-                      uint32_t nimg, int gray, int16_t* d_coefs, cudaStream_t st, uint32_t row0 = 0, uint32_t nrows = 0)
+                      uint32_t nimg, int gray, int16_t* d_coefs, cudaStream_t st, uint32_t row0 = 0, uint32_t nrows = 0,
+                      bool with_meta = false)
 {
     FwdParams p{};
     p.r = d_r, p.g = d_g, p.b = d_b;
@@ -287,6 +288,11 @@ static int launch_fwd(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g
     p.gray = gray;
     p.guard_counter = ctx->d_counters + 0;
     p.y_exact = ctx->d_y_exact;
+    if (with_meta && ctx->transform_variant != 1) {     // side information for launch_entropy (same context, same images)
+        int rc;
+        if ((rc = ctx->ensure(ctx->blk_meta, size_t(nimg) * (p.coef_stride >> 6) * 4))) return rc;
+        p.bmeta = static_cast<uint32_t*>(ctx->blk_meta.p) + size_t(row0) * p.HU * 6;
+    }
     if (ctx->transform_variant == 1) {
         dim3 grid((p.HU + kMcuPerCta - 1) / kMcuPerCta, p.VU, nimg);
         k_fwd_transform_f64<<<grid, kFwdThreads, 0, st>>>(p);
@@ -309,7 +315,7 @@ static int launch_fwd(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static int launch_entropy(jpezyb200_ctx* ctx, const int16_t* d_coefs, uint32_t W, uint32_t H, uint32_t nimg, uint8_t* d_scan,
-                          size_t slot_bytes, uint64_t* d_scan_bytes, uint64_t* d_scan_bits, cudaStream_t st)
+                          size_t slot_bytes, uint64_t* d_scan_bytes, uint64_t* d_scan_bits, cudaStream_t st, bool with_meta = false)
 {
     const uint32_t HU = mcu_units(W), VU = mcu_units(H);
     const size_t nmcu = size_t(HU) * VU;
@@ -317,6 +323,7 @@ static int launch_entropy(jpezyb200_ctx* ctx, const int16_t* d_coefs, uint32_t W
     EntParams p{};
     p.coefs = d_coefs;
     p.coef_stride = nmcu * 384;
+    p.bmeta = with_meta && ctx->transform_variant != 1 ? static_cast<const uint32_t*>(ctx->blk_meta.p) : nullptr;
     p.nblk = uint32_t(nmcu * 6);
     p.ntile = (p.nblk + kEntThreads - 1) / kEntThreads;
     p.uslot = round_up(slot_bytes + 64, 16);
@@ -390,8 +397,8 @@ int jpezyb200_encode_batch_dev(jpezyb200_ctx* ctx, const uint8_t* d_r, const uin
     const size_t ncoef = size_t(mcu_units(W)) * mcu_units(H) * 384 * nimg;
     if ((rc = ctx->ensure(ctx->coefs, ncoef * sizeof(int16_t)))) return rc;
     cudaStream_t st = pick_stream(ctx, stream);
-    if ((rc = launch_fwd(ctx, d_r, d_g, d_b, W, H, nimg, gray, static_cast<int16_t*>(ctx->coefs.p), st))) return rc;
-    return launch_entropy(ctx, static_cast<int16_t*>(ctx->coefs.p), W, H, nimg, d_scan, slot_bytes, d_scan_bytes, d_scan_bits, st);
+    if ((rc = launch_fwd(ctx, d_r, d_g, d_b, W, H, nimg, gray, static_cast<int16_t*>(ctx->coefs.p), st, 0, 0, true))) return rc;
+    return launch_entropy(ctx, static_cast<int16_t*>(ctx->coefs.p), W, H, nimg, d_scan, slot_bytes, d_scan_bytes, d_scan_bits, st, true);
 }
 
 int jpezyb200_encode(jpezyb200_ctx* ctx, const uint8_t* r, const uint8_t* g, const uint8_t* b, uint32_t W, uint32_t H, int gray,
@@ -427,9 +434,9 @@ int jpezyb200_encode(jpezyb200_ctx* ctx, const uint8_t* r, const uint8_t* g, con
         }
         JZ_CUDA_TRY(ctx, cudaEventRecord(hp->ev[k], hp->copy));
         JZ_CUDA_TRY(ctx, cudaStreamWaitEvent(st, hp->ev[k], 0));
-        if ((rc = launch_fwd(ctx, d_in, d_in + npx, d_in + 2 * npx, W, H, 1, gray, d_coefs, st, row0, row1 - row0))) return rc;
+        if ((rc = launch_fwd(ctx, d_in, d_in + npx, d_in + 2 * npx, W, H, 1, gray, d_coefs, st, row0, row1 - row0, true))) return rc;
     }
-    if ((rc = launch_entropy(ctx, d_coefs, W, H, 1, static_cast<uint8_t*>(ctx->scan_io.p), scan_cap, d_sz, d_sz + 1, st))) return rc;
+    if ((rc = launch_entropy(ctx, d_coefs, W, H, 1, static_cast<uint8_t*>(ctx->scan_io.p), scan_cap, d_sz, d_sz + 1, st, true))) return rc;
     uint64_t* h_sz = hp->h_sz;
     JZ_CUDA_TRY(ctx, cudaMemcpyAsync(h_sz, d_sz, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     JZ_CUDA_TRY(ctx, cudaStreamSynchronize(st));

@@ -22,6 +22,7 @@ constexpr int kStuffChunk = kStuffThreads * 16;
 struct EntParams {
     const int16_t* coefs;
     size_t coef_stride;      // int16 per image
+    const uint32_t* bmeta;   // nullptr, or [nimg][nblk] side information of the forward transform (FwdParams::bmeta)
     uint32_t nblk;           // blocks per image (6 * MCUs)
     uint32_t ntile;          // ceil(nblk / kEntThreads)
     uint32_t* blk_off;       // [nimg][nblk]   exclusive bit offset of the block within its tile
@@ -61,8 +62,28 @@ struct BlockRegs {
 #pragma unroll
         for (int i = 0; i < 8; ++i) q[i] = __ldg(reinterpret_cast<const int4*>(c) + i);
     }
+    // with the forward transform's side information: only the groups that hold a non-zero coefficient are fetched
+    __device__ __forceinline__ void load(const int16_t* __restrict__ c, uint32_t meta)
+    {
+        const uint32_t m = meta >> 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = (m >> i) & 1u ? __ldg(reinterpret_cast<const int4*>(c) + i) : make_int4(0, 0, 0, 0);
+        q[0].x = int((uint32_t(q[0].x) & 0xffff0000u) | (meta & 0xffffu));
+    }
     __device__ __forceinline__ int dc() const { return int(short(q[0].x & 0xffff)); }
 };
+// block b of an image and the predictor of its DC coefficient
+__device__ __forceinline__ void load_block(const int16_t* __restrict__ base, const uint32_t* __restrict__ meta, uint32_t b, long long pb,
+                                           int init, BlockRegs& blk, int& pred)
+{
+    if (meta) {
+        blk.load(base + size_t(b) * 64, __ldg(meta + b));
+        pred = pb >= 0 ? int(short(__ldg(meta + pb) & 0xffffu)) : init;
+    } else {
+        blk.load(base + size_t(b) * 64);
+        pred = pb >= 0 ? int(__ldg(base + size_t(pb) * 64)) : init;
+    }
+}
 
 // Visit the code words of one block in stream order.  emit(bits, nbits), nbits <= 27.
 template <class Emit>
@@ -147,8 +168,8 @@ __global__ void __launch_bounds__(kEntThreads) k_block_bits(const EntParams p)
         const int cls = (b % 6u) >= 4;
         const int comp = (b % 6u) < 4 ? 0 : int(b % 6u) - 3;
         BlockRegs blk;
-        blk.load(base + size_t(b) * 64);
-        const int pred = pb >= 0 ? int(__ldg(base + size_t(pb) * 64)) : (p.dc_init ? p.dc_init[img * 3 + comp] : 0);
+        int pred;
+        load_block(base, p.bmeta ? p.bmeta + img * p.nblk : nullptr, b, pb, p.dc_init ? p.dc_init[img * 3 + comp] : 0, blk, pred);
         encode_block(blk, pred, s_ac[cls], s_dc[cls], [&](uint32_t, int n) { bits += uint32_t(n); });
     }
     uint32_t total;
@@ -211,8 +232,8 @@ __global__ void __launch_bounds__(kEntThreads) k_scatter(const EntParams p)
     const int cls = (b % 6u) >= 4;
     const int comp = (b % 6u) < 4 ? 0 : int(b % 6u) - 3;
     BlockRegs blk;
-    blk.load(base + size_t(b) * 64);
-    const int pred = pb >= 0 ? int(__ldg(base + size_t(pb) * 64)) : (p.dc_init ? p.dc_init[img * 3 + comp] : 0);
+    int pred;
+    load_block(base, p.bmeta ? p.bmeta + img * p.nblk : nullptr, b, pb, p.dc_init ? p.dc_init[img * 3 + comp] : 0, blk, pred);
     const uint64_t pos = p.tile_base[img * p.ntile + blockIdx.x] + p.blk_off[img * p.nblk + b];
     uint32_t* out = reinterpret_cast<uint32_t*>(p.ustream + img * p.uslot) + (pos >> 5);
     uint64_t acc = 0;

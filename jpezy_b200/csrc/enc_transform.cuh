@@ -32,6 +32,9 @@ struct FwdParams {
     int gray;
     unsigned long long* guard_counter;
     const int8_t* y_exact;      // [65536] correction of the exact luma cases, indexed r | g << 8 (k_build_y_exact)
+    uint32_t* bmeta;            // nullptr, or per block (image stride coef_stride / 64): DC coefficient in bits 0..15, in bits
+                                // 16..23 which 8-coefficient zig-zag groups hold a non-zero AC coefficient -- the entropy coder
+                                // then reads only those groups of `coefs` (EntParams::bmeta)
 };
 
 // ---- colour conversion, bit-exact with src/encoder/jpezy_encoder.hpp:245-256 ------------------
@@ -769,7 +772,18 @@ __global__ void __launch_bounds__(256, V8 ? 4 : 2) k_fwd_transform_t(const FwdPa
     const uint32_t nvalid = min(uint32_t(kTileMcu), p.HU - mx0);
     const uint32_t nchunks = nvalid * 6 * 8;   // 16-byte chunks
     uint4* dst = reinterpret_cast<uint4*>(p.coefs + img * p.coef_stride + (size_t(my) * p.HU + mx0) * 384);
-    for (uint32_t c = t; c < nchunks; c += 256) dst[c] = *reinterpret_cast<const uint4*>(&s_out[(c >> 3) * kOutStride + (c & 7) * 16]);
+    uint32_t* meta = p.bmeta ? p.bmeta + img * (p.coef_stride >> 6) + (size_t(my) * p.HU + mx0) * 6 : nullptr;
+#pragma unroll
+    for (uint32_t c0 = 0; c0 < uint32_t(kTileBlk) * 8u; c0 += 256) {
+        const uint32_t c = c0 + uint32_t(t);
+        const uint4 v = *reinterpret_cast<const uint4*>(&s_out[(c >> 3) * kOutStride + (c & 7) * 16]);
+        if (c < nchunks) dst[c] = v;
+        if (meta) {
+            const bool nz = (((c & 7u) ? v.x : (v.x >> 16)) | v.y | v.z | v.w) != 0u;      // (group 0 without the DC coefficient)
+            const uint32_t nzb = __ballot_sync(0xffffffffu, nz);
+            if ((lane & 7) == 0 && c < nchunks) meta[c >> 3] = (v.x & 0xffffu) | (((nzb >> lane) & 0xffu) << 16);
+        }
+    }
 }
 
 }  // namespace jz

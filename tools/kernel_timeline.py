@@ -66,7 +66,7 @@ def main():
     order = []
     idx_in_step = 0
     for e in evs:
-        name = e.name.split("(")[0].replace("jz::", "")
+        name = e.name.split("(")[0].replace("jz::", "").replace("void ", "")
         if name.startswith("k_fwd_transform"):
             idx_in_step = 0
             prev_end = None
