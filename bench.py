@@ -399,10 +399,14 @@ def main():
         assert (d_in[0, 1, 0, : chk.shape[0]].cpu().numpy() == chk).all(), "device synth != host synth"
 
     h_nbytes = [None] * ring
+    h_pin = torch.empty((ring, B), dtype=torch.int64, pin_memory=True)
 
     def step(k):
         ctx.encode_batch_dev(d_in[k, 0], d_in[k, 1], d_in[k, 2], W, H, B, gray, d_scan[k], slot, d_nbytes[k], None, stream=sp)
-        nb = d_nbytes[k].cpu().numpy().astype(np.uint64)        # the decoder's input length is host knowledge (file size)
+        # the decoder's input length is host knowledge (a file size): read it back (pinned buffer, one stream synchronise)
+        h_pin[k].copy_(d_nbytes[k], non_blocking=True)
+        stream.synchronize()
+        nb = h_pin[k].numpy().view(np.uint64)
         h_nbytes[k] = nb
         ctx.decode_batch_dev(d_scan[k], slot, nb, B, frame, gray, d_out[k, 0], d_out[k, 1], d_out[k, 2], plane_len, d_status[k], stream=sp)
 

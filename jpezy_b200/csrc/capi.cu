@@ -298,13 +298,13 @@ static int launch_fwd(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g
         k_fwd_transform_f64<<<grid, kFwdThreads, 0, st>>>(p);
     } else {
         dim3 grid((p.HU + kTileMcu - 1) / kTileMcu, p.VU, nimg);
-        if (ctx->transform_variant == 2) k_fwd_transform_t<false><<<grid, 256, 0, st>>>(p);    // one thread per block (A/B runs)
+        if (ctx->transform_variant == 2) (void)jz_launch(k_fwd_transform_t<false>, grid, dim3(256), 0, st, p);    // one thread per block (A/B runs)
         else {
             if (!ctx->fwd_attr_set) {   // static + dynamic shared memory exceed 48 KiB: opt in once per context
                 JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdTrSmem));
                 ctx->fwd_attr_set = true;
             }
-            k_fwd_transform_t<true><<<grid, 256, kFwdTrSmem, st>>>(p);
+            (void)jz_launch(k_fwd_transform_t<true>, grid, dim3(256), kFwdTrSmem, st, p);
         }
     }
     ++ctx->launches;
@@ -351,15 +351,15 @@ static int launch_entropy(jpezyb200_ctx* ctx, const int16_t* d_coefs, uint32_t W
     p.ff_sum = static_cast<uint32_t*>(ctx->ff_sum.p);
     p.ff_base = static_cast<uint64_t*>(ctx->ff_base.p);
 
-    k_block_bits<<<dim3(p.ntile, nimg), kEntThreads, 0, st>>>(p);
-    k_scan_tiles<<<nimg, 1024, 0, st>>>(p);
+    (void)jz_launch(k_block_bits, dim3(p.ntile, nimg), dim3(kEntThreads), 0, st, p);
+    (void)jz_launch(k_scan_tiles, dim3(nimg), dim3(1024), 0, st, p);
     // grid-stride helpers: enough CTAs to fill the machine, split evenly over the images
     const uint32_t per_img = std::max<uint32_t>(1u, std::min<uint32_t>(p.nchunk, (148u * 8u + nimg - 1) / nimg));
-    k_zero_ustream<<<dim3(per_img, nimg), 256, 0, st>>>(p);
-    k_scatter<<<dim3(p.ntile, nimg), kEntThreads, 0, st>>>(p);
-    k_ff_count<<<dim3(per_img, nimg), kStuffThreads, 0, st>>>(p);
-    k_scan_ff<<<nimg, 1024, 0, st>>>(p);
-    k_stuff_write<<<dim3(per_img, nimg), kStuffThreads, 0, st>>>(p);
+    (void)jz_launch(k_zero_ustream, dim3(per_img, nimg), dim3(256), 0, st, p);
+    (void)jz_launch(k_scatter, dim3(p.ntile, nimg), dim3(kEntThreads), 0, st, p);
+    (void)jz_launch(k_ff_count, dim3(per_img, nimg), dim3(kStuffThreads), 0, st, p);
+    (void)jz_launch(k_scan_ff, dim3(nimg), dim3(1024), 0, st, p);
+    (void)jz_launch(k_stuff_write, dim3(per_img, nimg), dim3(kStuffThreads), 0, st, p);
     ctx->launches += 7;
     JZ_CUDA_TRY(ctx, cudaGetLastError());
     return JPEZYB200_OK;

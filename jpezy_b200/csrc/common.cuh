@@ -3,12 +3,38 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/jpezy_b200.h"
 #include "tables.h"
 
 namespace jz {
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the pipelines are chains of 10-20 short kernels on one stream, and on a single image
+// the gaps between them (kernel drain + launch latency) add up to more than a tenth of the step.  Every kernel starts
+// with pdl_wait() (griddepcontrol.wait: all prerequisite grids complete, their writes visible), so a launch made with
+// jz_launch() may be staged while its predecessor still runs.  The wait is a no-op for ordinary launches.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled()
+{
+    static const bool on = [] { const char* e = std::getenv("JPEZY_B200_PDL"); return !e || e[0] != '0'; }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t jz_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Constant bank: everything the transform kernels index with compile-time (uniform) indices.

@@ -363,6 +363,7 @@ __device__ __forceinline__ uint32_t cta_scan_excl(uint32_t v, uint32_t* s_warp, 
 
 __global__ void __launch_bounds__(kDecThreads) k_unstuff_count(const DecParams p)
 {
+    pdl_wait();
     __shared__ uint32_t s_warp[kDecThreads / 32];
     const size_t img = blockIdx.y;
     const uint64_t n = p.scan_bytes[img];
@@ -387,6 +388,7 @@ __global__ void __launch_bounds__(kDecThreads) k_unstuff_count(const DecParams p
 __global__ void __launch_bounds__(1024) k_scan_chunks(const uint32_t* __restrict__ cnt, uint64_t* __restrict__ base, uint32_t stride,
                                                       const uint64_t* __restrict__ nbytes, uint32_t unit, uint64_t* __restrict__ total_out)
 {
+    pdl_wait();
     __shared__ uint32_t s_warp[32];
     __shared__ uint64_t s_carry;
     const size_t img = blockIdx.x;
@@ -409,6 +411,7 @@ __global__ void __launch_bounds__(1024) k_scan_chunks(const uint32_t* __restrict
 
 __global__ void __launch_bounds__(kDecThreads) k_unstuff_write(const DecParams p)
 {
+    pdl_wait();
     __shared__ uint32_t s_warp[kDecThreads / 32];
     const size_t img = blockIdx.y;
     const uint64_t n = p.scan_bytes[img];
@@ -455,6 +458,7 @@ constexpr int kDecWarm = 32;
 
 __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, const int launch, const int host_poll)
 {
+    pdl_wait();
     extern __shared__ __align__(16) uint32_t s_span[];      // (kDecThreads * sub_bits / 8 + kSpanSlack) bytes of the stream
     __shared__ __align__(16) DecTabs s_tabs;
     __shared__ uint32_t s_state[kDecThreads];
@@ -556,6 +560,7 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
 // exclusive scan of the per-CTA block counts (in place) and per-image status
 __global__ void __launch_bounds__(1024) k_scan_blocks(const DecParams p, const uint32_t ncta)
 {
+    pdl_wait();
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     const size_t img = blockIdx.x;
@@ -590,6 +595,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const DecParams p, const u
 // ---- D1c: final pass, writes the non-zero coefficients (buffer pre-zeroed) ------------------------------
 __global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p)
 {
+    pdl_wait();
     extern __shared__ __align__(16) uint32_t s_span[];
     __shared__ __align__(16) DecTabs s_tabs;
     __shared__ uint32_t s_warp[kDecThreads / 32];
@@ -630,6 +636,7 @@ __global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p)
 // resets pred_dct[]; the segments between the markers were located by the un-stuffing pass (seg_start).
 __global__ void __launch_bounds__(128) k_decode_segments(const DecParams p)
 {
+    pdl_wait();
     __shared__ __align__(16) DecTabs s_tabs;
     load_dec_tabs(p.tabs, &s_tabs);
     __syncthreads();
@@ -700,6 +707,7 @@ __global__ void __launch_bounds__(128) k_decode_segments(const DecParams p)
 // tile = 256 MCUs; per tile the sums of the Y (ny blocks per MCU), Cb, Cr differences
 __global__ void __launch_bounds__(256) k_dc_sum(const DecParams p)
 {
+    pdl_wait();
     __shared__ int s_red[3][8];
     const size_t img = blockIdx.y;
     const uint32_t m = blockIdx.x * 256 + threadIdx.x;
@@ -726,6 +734,7 @@ __global__ void __launch_bounds__(256) k_dc_sum(const DecParams p)
 
 __global__ void __launch_bounds__(32) k_dc_scan_tiles(const DecParams p)
 {
+    pdl_wait();
     // one warp per (image, component): sequential over tiles in chunks of 32 with a shuffle scan
     const size_t img = blockIdx.x;
     const int comp = blockIdx.y;
@@ -746,6 +755,7 @@ __global__ void __launch_bounds__(32) k_dc_scan_tiles(const DecParams p)
 
 __global__ void __launch_bounds__(256) k_dc_apply(const DecParams p)
 {
+    pdl_wait();
     __shared__ int s_w[3][8];
     const size_t img = blockIdx.y;
     const uint32_t m = blockIdx.x * 256 + threadIdx.x;

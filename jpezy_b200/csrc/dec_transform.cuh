@@ -78,6 +78,7 @@ __device__ __forceinline__ uint8_t ref_B(int y, int cb) { return revise(__dadd_r
 // component's blocks, dup = max factor / component factor.
 __global__ void __launch_bounds__(kFwdThreads) k_inv_transform_f64(const InvParams p)
 {
+    pdl_wait();
     __shared__ int s_dq[kBlkPerCta][64];                 // dequantised, natural order
     __shared__ double s_tmp[kBlkPerCta][64];
     __shared__ short s_pix[kBlkPerCta][64];              // IDCT output (unclamped int, fits 16 bits)
@@ -411,6 +412,7 @@ __device__ __forceinline__ int sx_hi(uint32_t w) { return int(w) >> 16; }
 
 __global__ void __launch_bounds__(kInvThreads, 3) k_inv_transform(const __grid_constant__ InvParams p)
 {
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* s_coef = smem;                                  // [192][144] zig-zag int16 coefficients (padded); later the offset tables
     uint8_t* s_y = s_coef + kTileBlk * kOutStride;           // [16][kIYStride] int16 luma samples

@@ -154,6 +154,7 @@ __device__ __forceinline__ void load_lut(const HuffEncLut* __restrict__ g, uint3
 // ---- E3a ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEntThreads) k_block_bits(const EntParams p)
 {
+    pdl_wait();
     __shared__ uint32_t s_ac[2][256];
     __shared__ uint32_t s_dc[2][16];
     __shared__ uint32_t s_warp[kEntThreads / 32];
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(kEntThreads) k_block_bits(const EntParams p)
 // ---- E3b: one CTA per image, 64-bit running carry ------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_scan_tiles(const EntParams p)
 {
+    pdl_wait();
     __shared__ uint32_t s_warp[32];
     __shared__ uint64_t s_carry;
     const size_t img = blockIdx.x;
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const EntParams p)
 // ---- zero the part of the un-stuffed stream that will be written (grid-stride, data dependent) -----------
 __global__ void __launch_bounds__(256) k_zero_ustream(const EntParams p)
 {
+    pdl_wait();
     const size_t img = blockIdx.y;
     const uint64_t bits = p.img_bits[img];
     uint64_t n16 = ((bits + 7) / 8 + 15) / 16 + 1;   // 16-byte units, one spare for the pad byte
@@ -218,6 +221,7 @@ __global__ void __launch_bounds__(256) k_zero_ustream(const EntParams p)
 // ---- E3c ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEntThreads) k_scatter(const EntParams p)
 {
+    pdl_wait();
     __shared__ uint32_t s_ac[2][256];
     __shared__ uint32_t s_dc[2][16];
     load_lut(p.lut, s_ac, s_dc);
@@ -275,6 +279,7 @@ __device__ __forceinline__ uint32_t count_ff16(const uint4 v, uint64_t first_byt
 
 __global__ void __launch_bounds__(kStuffThreads) k_ff_count(const EntParams p)
 {
+    pdl_wait();
     __shared__ uint32_t s_warp[kStuffThreads / 32];
     const size_t img = blockIdx.y;
     const uint64_t nbytes = (p.img_bits[img] + 7) / 8;
@@ -293,6 +298,7 @@ __global__ void __launch_bounds__(kStuffThreads) k_ff_count(const EntParams p)
 
 __global__ void __launch_bounds__(1024) k_scan_ff(const EntParams p)
 {
+    pdl_wait();
     __shared__ uint32_t s_warp[32];
     __shared__ uint64_t s_carry;
     const size_t img = blockIdx.x;
@@ -324,6 +330,7 @@ __global__ void __launch_bounds__(1024) k_scan_ff(const EntParams p)
 
 __global__ void __launch_bounds__(kStuffThreads) k_stuff_write(const EntParams p)
 {
+    pdl_wait();
     __shared__ uint32_t s_warp[kStuffThreads / 32];
     const size_t img = blockIdx.y;
     const uint64_t nbytes = (p.img_bits[img] + 7) / 8;

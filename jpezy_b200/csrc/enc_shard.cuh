@@ -50,6 +50,7 @@ struct ShardParams {
 // last quantised DCs of the shard = predictors of the next shard's first Y / Cb / Cr blocks
 __global__ void k_shard_last_dc(const int16_t* __restrict__ coefs, uint32_t nmcu, int32_t* __restrict__ last_dc)
 {
+    pdl_wait();
     if (threadIdx.x < 3) {
         const int blk = threadIdx.x == 0 ? 3 : 3 + threadIdx.x;   // Y3, Cb, Cr
         last_dc[threadIdx.x] = coefs[(size_t(nmcu) - 1) * 384 + blk * 64];
@@ -58,6 +59,7 @@ __global__ void k_shard_last_dc(const int16_t* __restrict__ coefs, uint32_t nmcu
 
 __global__ void k_shard_info(const EntParams p, ShardInfo* __restrict__ info)
 {
+    pdl_wait();
     if (threadIdx.x == 0) {
         const uint64_t bits = p.img_bits[0];
         info->bits = bits;
@@ -67,6 +69,7 @@ __global__ void k_shard_info(const EntParams p, ShardInfo* __restrict__ info)
 
 __global__ void k_shard_geom(const ShardParams p)
 {
+    pdl_wait();
     if (threadIdx.x != 0) return;
     uint64_t base = 0;
     for (uint32_t j = 0; j < p.rank; ++j) base += p.all_info[j].bits;
@@ -108,6 +111,7 @@ __device__ __forceinline__ void load_owned16(const uint8_t* __restrict__ L, uint
 
 __global__ void __launch_bounds__(kStuffThreads) k_shard_ff_count(const ShardParams p)
 {
+    pdl_wait();
     __shared__ uint32_t s_warp[kStuffThreads / 32];
     const ShardGeom g = *p.geom;
     if (!g.fits) return;
@@ -129,6 +133,7 @@ __global__ void __launch_bounds__(kStuffThreads) k_shard_ff_count(const ShardPar
 
 __global__ void __launch_bounds__(1024) k_shard_scan_ff(const ShardParams p)
 {
+    pdl_wait();
     __shared__ uint32_t s_warp[32];
     __shared__ uint64_t s_carry;
     const ShardGeom g = *p.geom;
@@ -155,6 +160,7 @@ __global__ void __launch_bounds__(1024) k_shard_scan_ff(const ShardParams p)
 
 __global__ void __launch_bounds__(kStuffThreads) k_shard_stuff_write(const ShardParams p)
 {
+    pdl_wait();
     __shared__ uint32_t s_warp[kStuffThreads / 32];
     const ShardGeom g = *p.geom;
     uint64_t byte_base = 0, total = 0;
@@ -200,6 +206,7 @@ __global__ void __launch_bounds__(kStuffThreads) k_shard_stuff_write(const Shard
 // when dst lives on another GPU), single bytes only at the two ragged ends
 __global__ void __launch_bounds__(256) k_shard_push(const ShardParams p)
 {
+    pdl_wait();
     if (*p.overflow) return;
     uint64_t byte_base = 0;
     for (uint32_t j = 0; j < p.rank; ++j) byte_base += p.all_bytes[j];

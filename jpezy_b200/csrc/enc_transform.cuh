@@ -99,6 +99,7 @@ constexpr double kGuardF64 = 1e-6;   // fast-path FP64 error is < 1e-10; see DES
 // ---- validation build: FP64 separable DCT ---------------------------------------------------------
 __global__ void __launch_bounds__(kFwdThreads) k_fwd_transform_f64(const FwdParams p)
 {
+    pdl_wait();
     __shared__ __align__(16) int8_t s_pix[kBlkPerCta][64];
     __shared__ double s_tmp[kBlkPerCta][64];
     __shared__ __align__(16) int16_t s_out[kBlkPerCta][64];
@@ -270,6 +271,7 @@ __host__ __device__ constexpr int pack16(int lo, int hi) { return int((uint32_t(
 // decides; k_build_y_exact evaluates ref_Y once per (r, g) and stores (ref_Y + 128) - exact as a signed byte.
 __global__ void k_build_y_exact(int8_t* __restrict__ tbl)
 {
+    pdl_wait();
     const int r = blockIdx.x, g = threadIdx.x;
     int8_t corr = 0;
     for (int b = 0; b < 256; ++b) {
@@ -515,6 +517,7 @@ __device__ __forceinline__ const uint8_t* block_samples(const uint8_t* s_y, cons
 template <bool V8>
 __global__ void __launch_bounds__(256, V8 ? 4 : 2) k_fwd_transform_t(const FwdParams p)
 {
+    pdl_wait();
     extern __shared__ __align__(16) float s_tr[];                 // V8: [warp][block of the pass][8 rows x 8 + 8 pad] (kFwdTrSmem)
     __shared__ __align__(16) uint8_t s_y[16 * kYStride];
     __shared__ __align__(16) uint8_t s_cb[8 * kCStride];

@@ -38,6 +38,7 @@ __host__ __device__ inline uint8_t synth_pixel(int family, uint32_t W, uint32_t 
 __global__ void __launch_bounds__(256) k_synth(uint8_t* r, uint8_t* g, uint8_t* b, uint32_t W, uint32_t H, uint32_t first_frame,
                                                int family, uint32_t y0)
 {
+    pdl_wait();
     const size_t npx = size_t(W) * H;
     const size_t img = blockIdx.y;
     const uint32_t frame = first_frame + uint32_t(img);
