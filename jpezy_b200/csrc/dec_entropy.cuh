@@ -23,6 +23,7 @@
 namespace jz {
 
 constexpr int kDecThreads = 256;
+constexpr int kMaxSyncRounds = 66;   // entries of DecParams::changed
 constexpr int kLutBits = 10;
 
 // compact canonical decoder table for one DHT table, built on the host; entry layout:
@@ -75,6 +76,8 @@ struct DecParams {
     const uint8_t* scan;      // [nimg][slot]
     size_t slot;
     const uint64_t* scan_bytes;   // device copy of the host array [nimg]
+    uint64_t inline_bytes[8];     // ninline != 0 (small batches): the sizes travel as kernel arguments and k_unstuff_count
+    uint32_t ninline;             // fills scan_bytes itself -- no host-to-device copy in front of the first kernel
     // un-stuffed stream
     uint8_t* ustream;         // [nimg][uslot]  (uslot multiple of 16, 32 bytes of zero slack)
     size_t uslot;
@@ -366,7 +369,14 @@ __global__ void __launch_bounds__(kDecThreads) k_unstuff_count(const DecParams p
     pdl_wait();
     __shared__ uint32_t s_warp[kDecThreads / 32];
     const size_t img = blockIdx.y;
-    const uint64_t n = p.scan_bytes[img];
+    // first kernel of a decode: clears the counters of the synchronisation launches (no zero-fill between the kernels,
+    // which would break the chain of dependent launches)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && p.changed) {
+        if (threadIdx.x < kMaxSyncRounds) p.changed[threadIdx.x] = 0;
+        if (threadIdx.x < 2) p.iters_stat[threadIdx.x] = 0;
+    }
+    if (p.ninline && blockIdx.x == 0 && threadIdx.x == 0) const_cast<uint64_t*>(p.scan_bytes)[img] = p.inline_bytes[img & 7];
+    const uint64_t n = p.ninline ? p.inline_bytes[img & 7] : p.scan_bytes[img];
     const uint8_t* src = p.scan + img * p.slot;
     const uint32_t nch = uint32_t((n + 4095) / 4096);
     for (uint32_t ch = blockIdx.x; ch < nch; ch += gridDim.x) {
