@@ -272,8 +272,8 @@ __device__ __forceinline__ void aan_idct8_in4(float& d0, float& d1, float& d2, f
 }
 
 // dequantise one 16-byte group (8 zig-zag consecutive coefficients) into the natural-order register array
-template <int COMP, int GRP>
-__device__ __forceinline__ void dequant_group(const InvParams& p, const uint4 raw, float (&d)[64], float& gsum)
+template <int GRP>
+__device__ __forceinline__ void dequant_group(const float* __restrict__ M, const float* __restrict__ Wg, const uint4 raw, float (&d)[64], float& gsum)
 {
     const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
@@ -281,20 +281,23 @@ __device__ __forceinline__ void dequant_group(const InvParams& p, const uint4 ra
         const int nat = zz_at(GRP * 8 + h);
         const int c = (h & 1) ? (int(w[h >> 1]) >> 16) : int(short(w[h >> 1] & 0xffffu));
         const float cf = float(c);
-        d[nat] = cf * p.M[COMP][nat];
-        gsum = fmaf(fabsf(cf), p.Wg[COMP][nat], gsum);
+        d[nat] = cf * M[nat];
+        gsum = fmaf(fabsf(cf), Wg[nat], gsum);
     }
 }
 
 // dequantisation + IDCT of one block; `wm` = OR of the non-zero-group masks of the warp's blocks (warp uniform)
-template <int COMP>
-__device__ __forceinline__ void idct_block(const InvParams& p, const uint4* __restrict__ src, const uint4 raw0, const uint32_t wm, float (&d)[64],
-                                           float& gsum)
+// (comp is warp uniform: the tables are read from the constant bank with a uniform offset; one copy of the code for the
+// three components keeps the kernel's instruction footprint down)
+__device__ __forceinline__ void idct_block(const InvParams& p, const int comp, const uint4* __restrict__ src, const uint4 raw0, const uint32_t wm,
+                                           float (&d)[64], float& gsum)
 {
+    const float* __restrict__ M = p.M[comp];
+    const float* __restrict__ Wg = p.Wg[comp];
     gsum = 2e-5f;
     if (wm <= 1u) {
         // only zig-zag positions 0..7 = natural (0,0) (0,1) (1,0) (2,0) (1,1) (0,2) (0,3) (1,2): rows v <= 2, columns u <= 3
-        dequant_group<COMP, 0>(p, raw0, d, gsum);
+        dequant_group<0>(M, Wg, raw0, d, gsum);
         d[11] = d[17] = d[18] = d[19] = 0.0f;
         d[0] += 128.0f;   // level shift rides on the DC term (gain 1 through the flowgraph)
 #pragma unroll
@@ -306,14 +309,14 @@ __device__ __forceinline__ void idct_block(const InvParams& p, const uint4* __re
     }
 #pragma unroll
     for (int k = 0; k < 64; ++k) d[k] = 0.0f;
-    dequant_group<COMP, 0>(p, raw0, d, gsum);
-    if (wm & 0x02u) dequant_group<COMP, 1>(p, src[1], d, gsum);
-    if (wm & 0x04u) dequant_group<COMP, 2>(p, src[2], d, gsum);
-    if (wm & 0x08u) dequant_group<COMP, 3>(p, src[3], d, gsum);
-    if (wm & 0x10u) dequant_group<COMP, 4>(p, src[4], d, gsum);
-    if (wm & 0x20u) dequant_group<COMP, 5>(p, src[5], d, gsum);
-    if (wm & 0x40u) dequant_group<COMP, 6>(p, src[6], d, gsum);
-    if (wm & 0x80u) dequant_group<COMP, 7>(p, src[7], d, gsum);
+    dequant_group<0>(M, Wg, raw0, d, gsum);
+    if (wm & 0x02u) dequant_group<1>(M, Wg, src[1], d, gsum);
+    if (wm & 0x04u) dequant_group<2>(M, Wg, src[2], d, gsum);
+    if (wm & 0x08u) dequant_group<3>(M, Wg, src[3], d, gsum);
+    if (wm & 0x10u) dequant_group<4>(M, Wg, src[4], d, gsum);
+    if (wm & 0x20u) dequant_group<5>(M, Wg, src[5], d, gsum);
+    if (wm & 0x40u) dequant_group<6>(M, Wg, src[6], d, gsum);
+    if (wm & 0x80u) dequant_group<7>(M, Wg, src[7], d, gsum);
     d[0] += 128.0f;
 #pragma unroll
     for (int u = 0; u < 8; ++u) aan_idct8(d[u], d[8 + u], d[16 + u], d[24 + u], d[32 + u], d[40 + u], d[48 + u], d[56 + u]);
@@ -488,9 +491,7 @@ __global__ void __launch_bounds__(kInvThreads, 3) k_inv_transform(const __grid_c
             float d[64];
             float gsum;
             uint32_t dc_exact = 0;
-            if (warp < 4) idct_block<0>(p, src, raw0, wm, d, gsum);
-            else if (warp == 4) idct_block<1>(p, src, raw0, wm, d, gsum);
-            else idct_block<2>(p, src, raw0, wm, d, gsum);
+            idct_block(p, comp, src, raw0, wm, d, gsum);
             if (dc_only) {
                 // the exact value is very often an integer: ((c*c)*F)*1*1, /4, +128 exactly as the reference evaluates it
                 const double f = double(int(short(raw0.x & 0xffffu)) * int(p.qt[comp][0]));
