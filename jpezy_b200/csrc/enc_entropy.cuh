@@ -98,19 +98,31 @@ __device__ __forceinline__ void encode_block(const BlockRegs& blk, int dc_pred, 
         const uint32_t vbits = uint32_t(diff < 0 ? diff - 1 : diff) & ((1u << cat) - 1u);
         emit(((e >> 5) << cat) | vbits, int(e & 31u) + cat);
     }
-    // AC (:194-224)
+    // AC (:194-224).  Per 8-coefficient group a mask of the non-zero ones; the loop visits only those, so the code of
+    // emit() exists once per group instead of once per coefficient (the fully unrolled version was 78 KiB of code in
+    // k_scatter) and sparse blocks cost a few iterations.
     int run = 0;
     const uint32_t zrl = ac[0xf0], eob = ac[0x00];
 #pragma unroll
     for (int n8 = 0; n8 < 8; ++n8) {
         const int4 q = blk.q[n8];
         if (n8 && (q.x | q.y | q.z | q.w) == 0) { run += 8; continue; }
-        const int w[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t w[4] = {uint32_t(q.x), uint32_t(q.y), uint32_t(q.z), uint32_t(q.w)};
+        uint32_t m = 0;
 #pragma unroll
-        for (int h = 0; h < 8; ++h) {
-            if (n8 == 0 && h == 0) continue;
-            const int v = (h & 1) ? (w[h >> 1] >> 16) : int(short(w[h >> 1] & 0xffff));
-            if (v == 0) { ++run; continue; }
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t ne = __vsetne2(w[i], 0u);      // 1 in every non-zero halfword
+            m |= ((ne & 1u) | (ne >> 15)) << (2 * i);
+        }
+        if (n8 == 0) m &= ~1u;                            // the DC coefficient went first
+        int next = n8 == 0 ? 1 : 0;                        // first position of the group not yet accounted for (0 of group 0 = DC)
+        while (m) {
+            const int h = __ffs(int(m)) - 1;
+            m &= m - 1u;
+            run += h - next;
+            next = h + 1;
+            const uint32_t ww = (h >> 1) == 0 ? w[0] : ((h >> 1) == 1 ? w[1] : ((h >> 1) == 2 ? w[2] : w[3]));
+            const int v = (h & 1) ? (int(ww) >> 16) : int(short(ww & 0xffffu));
             while (run > 15) { emit(zrl >> 5, int(zrl & 31u)); run -= 16; }
             const int s = bit_length(abs(v));
             const uint32_t e = ac[(run << 4) | s];
@@ -118,6 +130,7 @@ __device__ __forceinline__ void encode_block(const BlockRegs& blk, int dc_pred, 
             emit(((e >> 5) << s) | vbits, int(e & 31u) + s);
             run = 0;
         }
+        run += 8 - next;
     }
     if (run) emit(eob >> 5, int(eob & 31u));   // coefficient 63 is zero <=> a run is pending
 }
