@@ -14,6 +14,7 @@ footprint exceeds the 126 MB L2 (see config.l2).
 """
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -421,6 +422,17 @@ def main():
     barrier()
     assert int(d_status.abs().sum().item()) == 0, "decode reported a corrupt stream"
     assert int((d_nbytes[: min(ring, args.warmup)] < 0).sum().item()) == 0, "entropy-coded segment overflowed its slot"
+    # the round trip must reproduce the picture (parity itself is the tests' job; this catches a step that does no work)
+    a = d_in[0, :, 0].reshape(3, H, W)[:, : min(H, 512)].float()
+    b = d_out[0, :, 0, : H * W].reshape(3, H, W)[:, : min(H, 512)].float() if (W % 16 == 0) else None
+    psnr = None
+    if b is not None:
+        if gray:
+            a = (0.299 * a[0] + 0.587 * a[1] + 0.114 * a[2]).unsqueeze(0)
+            b = b[:1]
+        mse = float(((a - b) ** 2).mean().item())
+        psnr = 10.0 * math.log10(255.0 ** 2 / max(mse, 1e-9))
+        assert psnr > (24.0 if args.family == 0 else 8.0), f"round trip PSNR {psnr:.1f} dB: the decoded frame is not the encoded one"
 
     sampler.mark = True
     l0 = ctx.stat(capi.STAT_KERNEL_LAUNCHES)
@@ -577,7 +589,7 @@ def main():
                                ring, ring * (in_bytes + out_bytes) / 1e6),
                            "sharding": "by image, no data-path collective"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "stages": stages}
+                "stages": stages, "roundtrip_psnr_db": psnr}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
