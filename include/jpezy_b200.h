@@ -106,6 +106,15 @@ JPEZYB200_API int jpezyb200_encode_batch_dev(jpezyb200_ctx* ctx, const uint8_t* 
                                uint32_t H, uint32_t nimg, int gray, uint8_t* d_scan, size_t slot_bytes,
                                uint64_t* d_scan_bytes, uint64_t* d_scan_bits, void* stream);
 
+/* Stuffed byte counts of a device-resident batch on the host: copies n values of d_values (d_scan_bytes or
+ * d_scan_bits of jpezyb200_encode_batch_dev / jpezyb200_entropy_encode_dev) into h_out through pinned memory of
+ * the context and returns when they have arrived -- i.e. when everything enqueued on `stream` before the call has
+ * finished.  This is the one host round trip of a device-resident encode -> decode chain: the decoder entry points
+ * take the segment lengths from the host (a JPEG decoder is handed a file of known size,
+ * src/decoder/jpezy_decoder.hpp:76-90), the encoder produces them on the device (bofstream's write cursor,
+ * src/encoder/jpezy_encoder.hpp:41-45,101-105). */
+JPEZYB200_API int jpezyb200_read_sizes(jpezyb200_ctx* ctx, const uint64_t* d_values, uint32_t n, uint64_t* h_out, void* stream);
+
 /* Batch of nimg images in HOST memory (image i: planes at r + i*W*H, segment at scan_out + i*slot_bytes, scan_bytes[i] = its
  * length, UINT64_MAX when it did not fit).  Pipelined over three streams: the host->device copies of one group of images,
  * the kernels of the previous group and the device->host copies of the one before overlap (pin the host buffers for the

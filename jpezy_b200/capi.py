@@ -17,7 +17,7 @@ EXPORTS = [
     "jpezyb200_decode", "jpezyb200_decode_batch_dev", "jpezyb200_entropy_decode_dev", "jpezyb200_transform_inv_dev",
     "jpezyb200_synth_dev", "jpezyb200_synth_rows_dev", "jpezyb200_shard_encode_a", "jpezyb200_shard_encode_b",
     "jpezyb200_shard_encode_c", "jpezyb200_shard_encode_d", "jpezyb200_ipc_alloc", "jpezyb200_ipc_open", "jpezyb200_ipc_close",
-    "jpezyb200_ipc_free", "jpezyb200_shard_decode_dev", "jpezyb200_encode_batch", "jpezyb200_decode_batch",
+    "jpezyb200_ipc_free", "jpezyb200_shard_decode_dev", "jpezyb200_encode_batch", "jpezyb200_decode_batch", "jpezyb200_read_sizes",
 ]
 
 
@@ -74,6 +74,7 @@ def load_library():
     L.jpezyb200_encode.argtypes = [vp, u8p, u8p, u8p, u32, u32, C.c_int, u8p, sz, C.POINTER(sz), C.POINTER(C.c_uint64)]
     L.jpezyb200_encode_batch_dev.argtypes = [vp, u8p, u8p, u8p, u32, u32, u32, C.c_int, u8p, sz, u64p, u64p, vp]
     L.jpezyb200_transform_fwd_dev.argtypes = [vp, u8p, u8p, u8p, u32, u32, u32, C.c_int, i16p, vp]
+    L.jpezyb200_read_sizes.argtypes = [vp, u64p, u32, u64p, vp]
     L.jpezyb200_entropy_encode_dev.argtypes = [vp, i16p, u32, u32, u32, C.c_int, u8p, sz, u64p, u64p, vp]
     L.jpezyb200_plane_bytes.argtypes = [C.POINTER(Frame)]
     L.jpezyb200_plane_bytes.restype = sz
@@ -190,6 +191,10 @@ class Context:
     def encode_batch_dev(self, d_r, d_g, d_b, W, H, nimg, gray, d_scan, slot_bytes, d_bytes=None, d_bits=None, stream=None):
         self._chk(self.lib.jpezyb200_encode_batch_dev(self.h, _dp(d_r), _dp(d_g), _dp(d_b), W, H, nimg, int(gray), _dp(d_scan),
                                                       slot_bytes, _dp(d_bytes), _dp(d_bits), stream))
+
+    def read_sizes(self, d_values, n, h_out, stream=None):
+        """n uint64 values of a device array into the numpy uint64 array h_out; returns when `stream` has reached this point"""
+        self._chk(self.lib.jpezyb200_read_sizes(self.h, _dp(d_values), n, _dp(h_out), stream))
 
     def transform_fwd_dev(self, d_r, d_g, d_b, W, H, nimg, gray, d_coefs, stream=None):
         self._chk(self.lib.jpezyb200_transform_fwd_dev(self.h, _dp(d_r), _dp(d_g), _dp(d_b), W, H, nimg, int(gray),

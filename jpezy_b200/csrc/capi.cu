@@ -178,6 +178,7 @@ void jpezyb200_ctx_destroy(jpezyb200_ctx* ctx)
     host_pipe_destroy(ctx);
     std::free(ctx->shard_state);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_sizes) cudaFreeHost(ctx->h_sizes);
     if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream), cudaStreamDestroy(ctx->aux_stream);
     if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
     if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
@@ -362,6 +363,19 @@ static int launch_entropy(jpezyb200_ctx* ctx, const int16_t* d_coefs, uint32_t W
     (void)jz_launch(k_stuff_write, dim3(per_img, nimg), dim3(kStuffThreads), 0, st, p);
     ctx->launches += 7;
     JZ_CUDA_TRY(ctx, cudaGetLastError());
+    return JPEZYB200_OK;
+}
+
+int jpezyb200_read_sizes(jpezyb200_ctx* ctx, const uint64_t* d_values, uint32_t n, uint64_t* h_out, void* stream)
+{
+    if (!ctx) return JPEZYB200_EINVAL;
+    if (!d_values || !h_out || n == 0 || n > 8192u) return ctx->fail(JPEZYB200_EINVAL, "null pointer / bad count");
+    JZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->h_sizes) JZ_CUDA_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_sizes), 8192 * sizeof(uint64_t)));
+    cudaStream_t st = pick_stream(ctx, stream);
+    JZ_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_sizes, d_values, size_t(n) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    JZ_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    std::memcpy(h_out, ctx->h_sizes, size_t(n) * sizeof(uint64_t));
     return JPEZYB200_OK;
 }
 

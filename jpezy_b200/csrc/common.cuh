@@ -113,6 +113,7 @@ struct jpezyb200_ctx {
     void* batch_pipe = nullptr;    // streams, events and double buffers of the pipelined host batches (capi_batch.inc)
     void* host_pipe = nullptr;     // copy stream and events of the band-pipelined single-image host entry points (capi.cu)
     void* shard_state = nullptr;   // host copy of the launch parameters between the phases (capi_shard.inc)
+    uint64_t* h_sizes = nullptr;   // pinned, 8192 values (jpezyb200_read_sizes)
     void* h_pinned = nullptr;
     size_t h_pinned_cap = 0;
 

@@ -473,6 +473,8 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     __shared__ __align__(16) DecTabs s_tabs;
     __shared__ uint32_t s_state[kDecThreads];
     __shared__ uint8_t s_chg[2][kDecThreads];
+    __shared__ uint16_t s_list[kDecThreads];      // subsequences to re-decode in this iteration
+    __shared__ uint32_t s_nlist;
     // launches are enqueued without host round trips: once a launch saw no change (a global fixed point), the
     // later ones return immediately (changed[] stays 0 for them, so the zero propagates to changed[rounds])
     // (host_poll: the host reads changed[1] after every launch instead)
@@ -531,30 +533,51 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     s_state[t] = st;
     s_chg[0][t] = chg ? 1 : 0;
     uint32_t nchanged = (launch > 0 && chg) ? 1u : 0u;
+    if (t == 0) s_nlist = 0;
     __syncthreads();
+    // The subsequences whose predecessor's end state changed are re-decoded from it.  Their set thins out quickly
+    // (a decode re-synchronises within its subsequence more often than not), so it is compacted first: entry j of the
+    // list is handled by thread j, and an iteration costs as many warps as there is work, not every warp that holds one
+    // such subsequence.
     for (int it = 0; it < 4 * kDecThreads; ++it) {     // (a chain cannot be longer than the CTA)
         // (the very first subsequence of the image has no predecessor: its guessed state is the true one)
         const bool redo = valid && isub > 0 && t > 0 && s_chg[it & 1][t - 1];
-        const uint32_t ps = redo ? s_state[t - 1] : 0u;
-        bool c2 = false;
-        if (redo) {
-            FastBits br;
-            br.init(span_sa, start + (ps & 63u));
-            uint32_t b = (ps >> 6) & 7u, z = (ps >> 9) & 63u, n = 0;
-            decode_span<false>(br, b, z, n, end, limit, &s_tabs, nullptr, nullptr, 0, 0, nullptr, p.nb, p.ny);
-            const uint32_t ns = pack_state(br.pos > end ? br.pos - end : 0u, b, z, n);
-            c2 = ((ns ^ st) & kStateSyncMask) != 0;
-            st = ns;
-        }
-        __syncthreads();                 // all reads of s_state[t-1] are done
-        if (redo) s_state[t] = st;
-        s_chg[(it + 1) & 1][t] = c2 ? 1 : 0;
-        if (c2 && owner) ++nchanged;
-        if (!__syncthreads_or(c2 ? 1 : 0)) {
-            if (t == 0 && launch <= 1) atomicMax(p.iters_stat + launch, (unsigned long long)(it + 1));
+        s_chg[(it + 1) & 1][t] = 0;      // (last read two barriers ago)
+        const uint32_t bal = __ballot_sync(0xffffffffu, redo);
+        uint32_t wbase = 0;
+        if ((t & 31) == 0 && bal) wbase = atomicAdd(&s_nlist, uint32_t(__popc(bal)));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (redo) s_list[wbase + __popc(bal & ((1u << (t & 31)) - 1u))] = uint16_t(t);
+        __syncthreads();
+        const uint32_t nlist = s_nlist;
+        if (nlist == 0) {
+            if (t == 0 && launch <= 1) atomicMax(p.iters_stat + launch, (unsigned long long)it);
             break;
         }
+        uint32_t tt = 0, ns = 0;
+        bool c2 = false;
+        if (uint32_t(t) < nlist) {
+            tt = s_list[t];
+            const uint32_t ps = s_state[tt - 1], old = s_state[tt];
+            const uint32_t start_tt = uint32_t(int64_t(tt) + int64_t(first_own) - kDecWarm - int64_t(first)) * p.sub_bits;   // as `start`
+            const uint32_t end_tt = start_tt + p.sub_bits;
+            FastBits br;
+            br.init(span_sa, start_tt + (ps & 63u));
+            uint32_t b = (ps >> 6) & 7u, z = (ps >> 9) & 63u, n = 0;
+            decode_span<false>(br, b, z, n, end_tt, limit, &s_tabs, nullptr, nullptr, 0, 0, nullptr, p.nb, p.ny);
+            ns = pack_state(br.pos > end_tt ? br.pos - end_tt : 0u, b, z, n);
+            c2 = ((ns ^ old) & kStateSyncMask) != 0;
+        }
+        __syncthreads();                 // all reads of s_state and s_list are done
+        if (uint32_t(t) < nlist) {
+            s_state[tt] = ns;
+            s_chg[(it + 1) & 1][tt] = c2 ? 1 : 0;
+            if (c2 && tt >= uint32_t(kDecWarm)) ++nchanged;      // an owned subsequence
+        }
+        if (t == 0) s_nlist = 0;
+        __syncthreads();
     }
+    st = s_state[t];
     const bool mine = valid && owner;
     if (mine) p.sub_state[si] = st;
     // the CTA's last valid subsequence is the seed of the next CTA

@@ -63,3 +63,38 @@ def test_batch_with_pinned_buffers_and_small_slots(ctx):
     for k in (0, 5, 11):
         want, _ = ctx.encode(r[k].numpy(), g[k].numpy(), b[k].numpy(), W, H)
         assert scans[k, : int(nbytes[k])].numpy().tobytes() == want
+
+
+def test_device_chain_with_read_sizes(ctx, oracle):
+    """encode_batch_dev -> read_sizes (the one host round trip) -> decode_batch_dev: the fused device-resident round trip of
+    bench.py; segments and decoded planes must equal the per-image host calls."""
+    W, H, N = 176, 144, 5
+    imgs = [J.synth.image(k % 3, W, H, frame=10 + k) for k in range(N)]
+    st = torch.cuda.Stream()
+    torch.cuda.set_stream(st)
+    try:
+        d_in = torch.from_numpy(np.stack([np.stack([im[c] for im in imgs]) for c in range(3)])).cuda()       # [3][N][H][W]
+        slot = W * H * 3
+        d_scan = torch.zeros((N, slot), dtype=torch.uint8, device="cuda")
+        d_nb = torch.zeros(N, dtype=torch.int64, device="cuda")
+        frame = J.default_frame(W, H)
+        pl = capi.plane_bytes(frame)
+        d_out = torch.full((3, N, pl), 0x55, dtype=torch.uint8, device="cuda")
+        d_st = torch.full((N,), -1, dtype=torch.int32, device="cuda")
+        ctx.encode_batch_dev(d_in[0], d_in[1], d_in[2], W, H, N, False, d_scan, slot, d_nb, None, stream=st.cuda_stream)
+        nb = np.zeros(N, dtype=np.uint64)
+        ctx.read_sizes(d_nb, N, nb, stream=st.cuda_stream)
+        assert (nb == d_nb.cpu().numpy().astype(np.uint64)).all()
+        ctx.decode_batch_dev(d_scan, slot, nb, N, frame, False, d_out[0], d_out[1], d_out[2], pl, d_st, stream=st.cuda_stream)
+        torch.cuda.synchronize()
+        assert (d_st.cpu().numpy() == 0).all()
+        scans, out = d_scan.cpu().numpy(), d_out.cpu().numpy()
+        for k, im in enumerate(imgs):
+            want, _ = ctx.encode(im[0], im[1], im[2], W, H)
+            assert scans[k, : int(nb[k])].tobytes() == want
+            if k == 0:
+                assert want == oracle.encode(im[0], im[1], im[2], W, H, scan_only=True)
+            r0, g0, b0 = ctx.decode(want, frame)
+            assert (out[0, k] == r0).all() and (out[1, k] == g0).all() and (out[2, k] == b0).all()
+    finally:
+        torch.cuda.set_stream(torch.cuda.default_stream())
