@@ -553,14 +553,84 @@ def main():
         for i in range(n_e2e):
             sb += e2e_step(i % nh)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt_seq = time.perf_counter() - t0
         sb /= n_e2e
-        e2e = {"value": world * B * npx * n_e2e / dt / 1e6, "unit": "MPix/s", "h2d_bytes_per_step": int(3 * npx * B + sb),
-               "d2h_bytes_per_step": int(sb + 3 * plane_len * B), "steps": n_e2e, "api": api}
+
+        # The same calls as a two-stage pipeline: while step i is decoded (device -> host is the long copy), step i + 1 is
+        # encoded (host -> device is the long copy) by a second host thread on a second context -- PCIe is full duplex and
+        # a context is used by one thread at a time (SURVEY.md 8b "Threading").  Every step still carries its own
+        # host-to-device copy of the input planes and device-to-host copy of the decoded planes.
+        ctx2 = J.Context(local_rank)
+        if B == 1:
+            hscan2 = [hscan, torch.empty_like(hscan).pin_memory()]
+            nb2 = [C.c_size_t(0), C.c_size_t(0)]
+
+            def enc_stage(i):
+                ctx._chk(L.jpezyb200_encode(ctx.h, hin[i % nh][0].data_ptr(), hin[i % nh][1].data_ptr(), hin[i % nh][2].data_ptr(), W, H,
+                                            int(gray), hscan2[i & 1].data_ptr(), hscan2[i & 1].numel(), C.byref(nb2[i & 1]), C.byref(nbits_c)))
+
+            def dec_stage(i):
+                ctx2._chk(L.jpezyb200_decode(ctx2.h, hscan2[i & 1].data_ptr(), nb2[i & 1].value, C.byref(frame), int(gray),
+                                             hout[0].data_ptr(), hout[1].data_ptr(), hout[2].data_ptr(), plane_len))
+        else:
+            hscan2 = [hscan, torch.empty_like(hscan).pin_memory()]
+            hnb2 = [hnb, np.zeros_like(hnb)]
+
+            def enc_stage(i):
+                ctx.encode_batch(hin[i % nh][0], hin[i % nh][1], hin[i % nh][2], W, H, B, gray, hscan2[i & 1], hslot, hnb2[i & 1])
+
+            def dec_stage(i):
+                ctx2.decode_batch(hscan2[i & 1], hslot, hnb2[i & 1], B, frame, gray, hout[0], hout[1], hout[2], plane_len, hst)
+                assert not hst.any()
+        n_pipe = 2 * n_e2e
+        gate = threading.Barrier(2)
+        errs = []
+
+        def dec_worker():
+            try:
+                torch.cuda.set_device(local_rank)
+                for i in range(n_pipe + 1):
+                    if i >= 1:
+                        dec_stage(i - 1)
+                    gate.wait()
+            except Exception as ex:      # noqa: BLE001
+                errs.append(ex)
+                gate.abort()
+
+        enc_stage(0), dec_stage(0)       # warm the second context
+        barrier()
+        th = threading.Thread(target=dec_worker)
+        t0 = time.perf_counter()
+        th.start()
+        try:
+            for i in range(n_pipe + 1):
+                if i < n_pipe:
+                    enc_stage(i)
+                gate.wait()
+        except threading.BrokenBarrierError:
+            pass
+        except Exception:
+            gate.abort()
+            th.join()
+            raise
+        th.join()
+        torch.cuda.synchronize()
+        dt_pipe = time.perf_counter() - t0
+        if errs:
+            raise errs[0]
+        ctx2.close()
+        dts = [dt_seq, dt_pipe]
+        if dist is not None:
+            t = torch.tensor(dts, device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dts = [float(x) for x in t.tolist()]
+        v_seq = world * B * npx * n_e2e / dts[0] / 1e6
+        v_pipe = world * B * npx * n_pipe / dts[1] / 1e6
+        e2e = {"value": v_pipe, "unit": "MPix/s", "h2d_bytes_per_step": int(3 * npx * B + sb),
+               "d2h_bytes_per_step": int(sb + 3 * plane_len * B), "steps": n_pipe,
+               "api": api + "; two-stage host pipeline: step i+1 is encoded (context 1, host thread 1) while step i is decoded "
+                            "(context 2, host thread 2), every step with its own H2D and D2H copies",
+               "one_call_after_the_other": {"value": v_seq, "unit": "MPix/s", "steps": n_e2e}}
 
     sampler.stop_flag = True
     clocks = sampler.summary()
