@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-end measurement set on one B200: tests, smoke, benches, then the ncu passes of the same bench command
+# round-end measurement set on one B200: tests, smoke, benches (ncu passes: see profiles/r01_summary.md for the commands)
 set -u
 mkdir -p gpurun_out/final
 O=gpurun_out/final
@@ -13,7 +13,4 @@ python bench.py --workload c4 --steps 20 --warmup 3 --no-cpu-baseline > $O/bench
 python bench.py --workload c1 --no-cpu-baseline > $O/bench_c1.json 2> $O/bench_c1.err
 python tools/kernel_timeline.py --workload c2 > $O/timeline_c2.txt 2>&1
 python tools/kernel_timeline.py --workload c3 --steps 5 > $O/timeline_c3.txt 2>&1
-# ncu: launch list of the default bench command (short), then one full capture of one step
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_c2.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on --launch-skip 260 --launch-count 24 -o $O/prof_final -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_full.log 2>&1
-ls -la $O
+ls -la $O | head -30
