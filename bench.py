@@ -583,19 +583,24 @@ def main():
                 ctx2.decode_batch(hscan2[i & 1], hslot, hnb2[i & 1], B, frame, gray, hout[0], hout[1], hout[2], plane_len, hst)
                 assert not hst.any()
         n_pipe = 2 * n_e2e
-        gate = threading.Barrier(2)
+        # two scan buffers between the stages: the encoder may run up to two steps ahead of the decoder
+        filled = [threading.Semaphore(0), threading.Semaphore(0)]
+        free = [threading.Semaphore(1), threading.Semaphore(1)]
         errs = []
 
         def dec_worker():
             try:
                 torch.cuda.set_device(local_rank)
-                for i in range(n_pipe + 1):
-                    if i >= 1:
-                        dec_stage(i - 1)
-                    gate.wait()
+                for i in range(n_pipe):
+                    filled[i & 1].acquire()
+                    if errs:
+                        return
+                    dec_stage(i)
+                    free[i & 1].release()
             except Exception as ex:      # noqa: BLE001
                 errs.append(ex)
-                gate.abort()
+                for sem in free:
+                    sem.release()
 
         enc_stage(0), dec_stage(0)       # warm the second context
         barrier()
@@ -603,16 +608,16 @@ def main():
         t0 = time.perf_counter()
         th.start()
         try:
-            for i in range(n_pipe + 1):
-                if i < n_pipe:
-                    enc_stage(i)
-                gate.wait()
-        except threading.BrokenBarrierError:
-            pass
-        except Exception:
-            gate.abort()
-            th.join()
-            raise
+            for i in range(n_pipe):
+                free[i & 1].acquire()
+                if errs:
+                    break
+                enc_stage(i)
+                filled[i & 1].release()
+        except Exception as ex:      # noqa: BLE001
+            errs.append(ex)
+            for sem in filled:
+                sem.release()
         th.join()
         torch.cuda.synchronize()
         dt_pipe = time.perf_counter() - t0
