@@ -1,3 +1,6 @@
+"""A/B run of the transform kernels on 64 HD frames: JPEZYB200_OPT_TRANSFORM = 2 selects the one-thread-per-block forward
+kernel (the inverse kernel has a single production variant; its time is printed as a repeatability check).
+usage: python tools/ab_transform.py [family]"""
 import sys, os
 sys.path.insert(0, "/root/repo")
 import numpy as np, torch
