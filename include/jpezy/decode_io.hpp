@@ -3,8 +3,10 @@
 #ifndef JPEZY_B200_DECODE_IO_HPP
 #define JPEZY_B200_DECODE_IO_HPP
 
+#include <algorithm>
 #include <ostream>
 #include <string>
+#include <vector>
 
 #include "pnm_stream.hpp"
 
@@ -22,17 +24,16 @@ private:
     {
         if (!io.initializing_succeed) io.report_error(__func__);
         const std::size_t n = io.width * io.height;
-        std::string out = "P3\n# Decoded by jpezy\n" + std::to_string(io.width) + " " + std::to_string(io.height) + "\n" + std::to_string(io.max_color) + "\n";
-        out.reserve(out.size() + n * 12);
-        char tmp[16];
-        const auto put = [&](unsigned v, char sep) {
-            int k = 0;
-            do tmp[k++] = char('0' + v % 10), v /= 10; while (v);
-            while (k) out.push_back(tmp[--k]);
-            out.push_back(sep);
-        };
-        for (std::size_t i = 0; i < n && i < io.r_.size(); ++i) put(unsigned(io.r_[i]), ' '), put(unsigned(io.g_[i]), ' '), put(unsigned(io.b_[i]), '\n');
-        ofs.write(out.data(), std::streamsize(out.size()));
+        const std::string head = "P3\n# Decoded by jpezy\n" + std::to_string(io.width) + " " + std::to_string(io.height) + "\n" + std::to_string(io.max_color) + "\n";
+        ofs.write(head.data(), std::streamsize(head.size()));
+        const std::size_t m = std::min(n, io.r_.size());
+        // the ASCII formatting is the decoder CLI's bottleneck (12 bytes out per pixel): ranges of pixels on the host's cores
+        const unsigned parts = pnm_detail::host_threads(m * 12);
+        std::vector<std::string> chunk(parts);
+        pnm_detail::parallel_parts(parts, [&](unsigned k) {
+            pnm_detail::format_triples(io.r_, io.g_, io.b_, m * k / parts, m * (k + 1) / parts, chunk[k]);
+        });
+        for (const std::string& c : chunk) ofs.write(c.data(), std::streamsize(c.size()));
         return ofs;
     }
     const Range &r_, &g_, &b_;

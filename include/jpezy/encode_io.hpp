@@ -7,6 +7,7 @@
 #ifndef JPEZY_B200_ENCODE_IO_HPP
 #define JPEZY_B200_ENCODE_IO_HPP
 
+#include <algorithm>
 #include <cctype>
 #include <cstring>
 #include <fstream>
@@ -33,23 +34,18 @@ inline constexpr gray_scale_t gray_scale{};
 struct encode_io : pnm_stream {
     encode_io(const char* file_name) : pnm_stream(true, 0, 0, 0)
     {
-        // the whole file in one read; lines are cut out of the buffer with std::getline's rules
-        std::string buf;
-        {
-            std::ifstream ifs(file_name, std::ios::binary);
-            if (!ifs) {
-                initializing_succeed = false;
-                return;
-            }
-            ifs.seekg(0, std::ios::end);
-            const std::streamoff n = ifs.tellg();
-            ifs.seekg(0, std::ios::beg);
-            if (n > 0) {
-                buf.resize(std::size_t(n));
-                ifs.read(&buf[0], n);
-                buf.resize(std::size_t(ifs.gcount()));
-            }
+        // the whole file mapped; lines are cut out of it with std::getline's rules
+        const pnm_detail::file_view fv(file_name);
+        if (!fv.ok) {
+            initializing_succeed = false;
+            return;
         }
+        const struct {
+            const char* p;
+            std::size_t n;
+            const char* data() const { return p; }
+            std::size_t size() const { return n; }
+        } buf{fv.data ? fv.data : "", fv.size};
         std::size_t pos = 0;
         bool eof = false;
         // std::getline: a line ends at '\n'; reaching the end of the data while reading sets eof (and the text read so far
@@ -115,16 +111,51 @@ struct encode_io : pnm_stream {
             width = std::size_t(to_int(wh[0])), height = std::size_t(to_int(wh[1]));
             format = jump_comment();
             max_color = std::size_t(std::stoi(std::string(format)));      // whole line through stoi (leading blanks allowed)
-            std::vector<value_type> img;
-            img.reserve(width * height * 3);
-            for (std::string_view line = jump_comment(); !eof; line = jump_comment()) {
-                // exactly one trailing empty token is forgiven (:83-84), every other one reaches stoi
-                for_each_token(line, [&](std::string_view t, bool last) {
-                    if (!(last && t.empty())) img.push_back(value_type(to_int(t)));
-                });
+            // The pixel lines.  Only lines that end in '\n' are data (the reference's loop tests eof after reading a line,
+            // :80), lines containing '#' are dropped whole.  The body is cut at line starts into one range per host
+            // thread; a token std::stoi rejects throws exactly as in a sequential pass (first one in file order).
+            const char* const body = buf.data() + pos;
+            const std::size_t blen = buf.size() - pos;
+            const unsigned parts = pnm_detail::host_threads(blen);
+            std::vector<std::size_t> cut(parts + 1, blen);
+            cut[0] = 0;
+            for (unsigned k = 1; k < parts; ++k) {
+                const std::size_t from = std::max(cut[k - 1], blen * k / parts);
+                const void* nl = from < blen ? std::memchr(body + from, '\n', blen - from) : nullptr;
+                cut[k] = nl ? std::size_t(static_cast<const char*>(nl) - body) + 1 : blen;
             }
-            rgb_img.resize(img.size() / 3);
-            for (std::size_t k = 0; k < rgb_img.size(); ++k) rgb_img[k] = {img[3 * k], img[3 * k + 1], img[3 * k + 2]};
+            std::vector<std::vector<value_type>> part(parts);
+            pnm_detail::parallel_parts(parts, [&](unsigned k) {
+                std::vector<value_type> img;      // (local: the vector headers in `part` share cache lines)
+                img.reserve((cut[k + 1] - cut[k]) / 2);
+                const char* p = body + cut[k];
+                const char* const e = body + cut[k + 1];
+                while (p < e) {
+                    const void* nl = std::memchr(p, '\n', std::size_t(e - p));
+                    if (!nl) break;                                  // unterminated last line of the file: dropped
+                    const std::string_view line(p, std::size_t(static_cast<const char*>(nl) - p));
+                    p = static_cast<const char*>(nl) + 1;
+                    if (line.find('#') != std::string_view::npos) continue;
+                    // exactly one trailing empty token is forgiven (:83-84), every other one reaches stoi
+                    for_each_token(line, [&](std::string_view t, bool last) {
+                        if (!(last && t.empty())) img.push_back(value_type(to_int(t)));
+                    });
+                }
+                part[k] = std::move(img);
+            });
+            std::size_t total = 0;
+            for (const auto& v : part) total += v.size();
+            rgb_img.resize(total / 3);
+            // std::array<byte, 3> is three contiguous bytes: the parts are laid end to end, the incomplete last triple is cut
+            {
+                unsigned char* dst = reinterpret_cast<unsigned char*>(rgb_img.data());
+                std::size_t room = rgb_img.size() * 3;
+                for (const auto& v : part) {
+                    const std::size_t n = std::min(room, v.size());
+                    if (n) std::memcpy(dst, v.data(), n);
+                    dst += n, room -= n;
+                }
+            }
         }
         std::cout << "width: " << width << " height: " << height << std::endl;
     }
@@ -134,16 +165,19 @@ private:
     friend std::ostream& operator<<(std::ostream& os, const encode_io& pnm)
     {
         pnm.report_error(__func__);
-        std::string out = "P3\n" + std::to_string(pnm.width) + " " + std::to_string(pnm.height) + "\n" + std::to_string(pnm.max_color) + "\n";
-        out.reserve(out.size() + pnm.rgb_img.size() * 12);
-        const auto put = [&out](unsigned v, char sep) {
-            if (v >= 100) out.push_back(char('0' + v / 100));
-            if (v >= 10) out.push_back(char('0' + v / 10 % 10));
-            out.push_back(char('0' + v % 10));
-            out.push_back(sep);
+        const std::string head = "P3\n" + std::to_string(pnm.width) + " " + std::to_string(pnm.height) + "\n" + std::to_string(pnm.max_color) + "\n";
+        os.write(head.data(), std::streamsize(head.size()));
+        const std::size_t n = pnm.rgb_img.size();
+        const unsigned parts = pnm_detail::host_threads(n * 12);
+        std::vector<std::string> chunk(parts);
+        struct plane {      // view of one channel of the interleaved image
+            const std::array<rgb_type, 3>* px;
+            int c;
+            unsigned operator[](std::size_t i) const { return unsigned(px[i][c]); }
         };
-        for (const auto& rgb : pnm.rgb_img) put(rgb[0], ' '), put(rgb[1], ' '), put(rgb[2], '\n');
-        os.write(out.data(), std::streamsize(out.size()));
+        const plane r{pnm.rgb_img.data(), 0}, g{pnm.rgb_img.data(), 1}, b{pnm.rgb_img.data(), 2};
+        pnm_detail::parallel_parts(parts, [&](unsigned k) { pnm_detail::format_triples(r, g, b, n * k / parts, n * (k + 1) / parts, chunk[k]); });
+        for (const std::string& c : chunk) os.write(c.data(), std::streamsize(c.size()));
         return os;
     }
 

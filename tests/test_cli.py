@@ -85,6 +85,64 @@ def test_p3_reader_grammar_matches_reference_cli(tmp_path, name):
         assert (tmp_path / "ref.ppm").read_text() == (tmp_path / "mine.ppm").read_text()
 
 
+def _big_ppm(seed, bad_at=None, tail_newline=True):
+    """~2.5 MB of pixel lines (above the reader's 1 MiB threshold for splitting the body over the host's cores) with the
+    grammar's quirks sprinkled in: comment lines, data lines with '#', trailing blanks, tabs, CRLF, several pixels per line"""
+    rng = np.random.default_rng(seed)
+    W, H = 640, 330
+    vals = rng.integers(0, 256, size=W * H * 3)
+    out = ["P3\n# made for the test\n%d %d\n255\n" % (W, H)]
+    i, n, line_no = 0, len(vals), 0
+    while i < n:
+        k = int(rng.integers(1, 13)) * 3 if line_no % 7 else 3
+        toks = [str(v) for v in vals[i:i + k]]
+        i += k
+        sep = "\t" if line_no % 11 == 3 else " "
+        line = sep.join(toks)
+        if line_no % 13 == 5:
+            line += " "                      # one trailing blank is forgiven
+        if line_no % 17 == 9:
+            line += "\r"                     # CRLF: the '\r' separates a trailing empty token
+        out.append(line + "\n")
+        if line_no % 19 == 4:
+            out.append("# comment between the data lines\n")
+        if line_no % 23 == 6:
+            out.append("1 2 3 # a data line with a hash is dropped whole\n")
+        if bad_at is not None and line_no == bad_at:
+            out.append("4  5 6\n")            # interior empty token: std::stoi throws
+        line_no += 1
+    text = "".join(out)
+    return text if tail_newline else text + "7 8 9"
+
+
+@needs_ref
+@pytest.mark.parametrize("case", ["clean", "no_final_newline", "bad_token_early", "bad_token_late"])
+def test_p3_reader_on_a_file_split_over_host_threads(tmp_path, case):
+    """the multi-threaded reader / echo writer must behave like the reference's sequential ones, exceptions included"""
+    ref = orc.Reference()
+    text = {"clean": lambda: _big_ppm(1), "no_final_newline": lambda: _big_ppm(2, tail_newline=False),
+            "bad_token_early": lambda: _big_ppm(3, bad_at=40), "bad_token_late": lambda: _big_ppm(4, bad_at=20000)}[case]()
+    assert len(text) > (1 << 20)
+    src = tmp_path / "in.ppm"
+    src.write_text(text)
+    a = run(ref.encode_exe, str(src), str(tmp_path / "ref.ppm"))
+    b = run(ENC, str(src), str(tmp_path / "mine.ppm"))
+    assert a.returncode == b.returncode
+    assert strip_times(a.stdout) == strip_times(b.stdout) and a.stderr == b.stderr
+    if a.returncode == 0:
+        assert (tmp_path / "ref.ppm").read_bytes() == (tmp_path / "mine.ppm").read_bytes()
+
+
+def test_decode_io_writer_host_only(tmp_path):
+    """the decoder CLI's P3 writer, single- and multi-threaded, against a plain iostream rendering (no device needed)"""
+    exe = tmp_path / "decode_io_check"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-I" + os.path.join(ROOT, "include"),
+                           "-o", str(exe), os.path.join(ROOT, "tests", "host", "decode_io_check.cpp")])
+    p = run(str(exe))
+    assert p.returncode == 0, p.stdout
+    assert p.stdout.count(" ok ") == 4
+
+
 def test_no_cpu_fallback(tmp_path):
     import torch
     if torch.cuda.is_available():
