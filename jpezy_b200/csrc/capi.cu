@@ -14,6 +14,7 @@
 #include "dec_transform.cuh"
 #include "enc_entropy.cuh"
 #include "enc_transform.cuh"
+#include "enc_transform2.cuh"
 #include "enc_shard.cuh"
 #include "synth.cuh"
 
@@ -137,6 +138,27 @@ int jpezyb200_ctx_create(int device, jpezyb200_ctx** out)
             }
             JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(gQcol, col, sizeof col));
             JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(gIzzCol, izzc, sizeof izzc));
+            // second-generation forward kernel (enc_transform2.cuh): (K, K) pairs per (class, column); the DC multiplier
+            // carries 1 - 2^-20 so that trunc(S * K) reproduces int(int(((S*c)*c)/4)/q) for every sum S; class 2 = zeros
+            Q2Col q2[3][8];
+            float g2[2][8][8], thr[3];
+            std::memset(q2, 0, sizeof q2);
+            for (int c = 0; c < 2; ++c) {
+                double gmax = 0.0;
+                for (int j = 0; j < 8; ++j)
+                    for (int i = 0; i < 8; ++i) {
+                        float K = qc.K[c][i * 8 + j];
+                        if ((i | j) == 0) K = float((1.0 - 1.0 / 1048576.0) / (8.0 * (c ? kQuantChroma[0] : kQuantLuma[0])));
+                        else gmax = std::max(gmax, double(qc.G[c][i * 8 + j]));
+                        q2[c][j].K[i] = make_float2(K, K);
+                        g2[c][j][i] = qc.G[c][i * 8 + j];
+                    }
+                thr[c] = float(1.0 - 2.0 * gmax);
+            }
+            thr[2] = 3.0e38f;
+            JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(gQ2K, q2, sizeof q2));
+            JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(gQ2G, g2, sizeof g2));
+            JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(gQ2Thr, thr, sizeof thr));
         }
         HuffEncLut lut[2];
         build_enc_lut(kDcLuma, kAcLuma, &lut[0]);
@@ -273,6 +295,46 @@ static int check_geometry(jpezyb200_ctx* ctx, uint32_t W, uint32_t H, uint32_t n
     return JPEZYB200_OK;
 }
 
+// the bulk copies of k_fwd_transform2 move whole 16-byte units: every pixel row and the coefficient buffer must start on one
+static bool fwd2_ok(const FwdParams& p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p.r) | reinterpret_cast<uintptr_t>(p.g) | reinterpret_cast<uintptr_t>(p.b) |
+                        reinterpret_cast<uintptr_t>(p.coefs);
+    return (p.W & 15u) == 0 && (a & 15u) == 0 && (p.plane_stride & 15u) == 0;
+}
+
+// picks the forward-transform kernel for the parameters (JPEZYB200_OPT_TRANSFORM, alignment) and launches it
+static int launch_fwd_kernel(jpezyb200_ctx* ctx, const FwdParams& p, uint32_t nimg, cudaStream_t st)
+{
+    if (ctx->transform_variant == 1) {
+        dim3 grid((p.HU + kMcuPerCta - 1) / kMcuPerCta, p.VU, nimg);
+        k_fwd_transform_f64<<<grid, kFwdThreads, 0, st>>>(p);
+    } else if (ctx->transform_variant == 0 && fwd2_ok(p)) {
+        // second-generation kernel: rows fetched by bulk copies, needs 16-byte aligned rows and buffers
+        static const int tile_mcu = [] { const char* e = std::getenv("JPEZY_B200_FWD_TILE"); return e && std::atoi(e) == 16 ? 16 : 8; }();
+        if (!ctx->fwd2_attr_set) {
+            JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2<8>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2<16>::kSmem));
+            ctx->fwd2_attr_set = true;
+        }
+        if (tile_mcu == 16) (void)jz_launch(k_fwd_transform2<16>, dim3((p.HU + 15) / 16, p.VU, nimg), dim3(Fwd2<16>::kThreads), Fwd2<16>::kSmem, st, p);
+        else (void)jz_launch(k_fwd_transform2<8>, dim3((p.HU + 7) / 8, p.VU, nimg), dim3(Fwd2<8>::kThreads), Fwd2<8>::kSmem, st, p);
+    } else {
+        dim3 grid((p.HU + kTileMcu - 1) / kTileMcu, p.VU, nimg);
+        if (ctx->transform_variant == 2) (void)jz_launch(k_fwd_transform_t<false>, grid, dim3(256), 0, st, p);    // one thread per block (A/B runs)
+        else {
+            if (!ctx->fwd_attr_set) {   // static + dynamic shared memory exceed 48 KiB: opt in once per context
+                JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdTrSmem));
+                ctx->fwd_attr_set = true;
+            }
+            (void)jz_launch(k_fwd_transform_t<true>, grid, dim3(256), kFwdTrSmem, st, p);
+        }
+    }
+    ++ctx->launches;
+    JZ_CUDA_TRY(ctx, cudaGetLastError());
+    return JPEZYB200_OK;
+}
+
 // rows: MCU rows [row0, row0 + nrows) only (nrows == 0: all); the planes always hold the whole image
 static int launch_fwd(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g, const uint8_t* d_b, uint32_t W, uint32_t H,
                       uint32_t nimg, int gray, int16_t* d_coefs, cudaStream_t st, uint32_t row0 = 0, uint32_t nrows = 0,
@@ -294,23 +356,7 @@ static int launch_fwd(jpezyb200_ctx* ctx, const uint8_t* d_r, const uint8_t* d_g
         if ((rc = ctx->ensure(ctx->blk_meta, size_t(nimg) * (p.coef_stride >> 6) * 4))) return rc;
         p.bmeta = static_cast<uint32_t*>(ctx->blk_meta.p) + size_t(row0) * p.HU * 6;
     }
-    if (ctx->transform_variant == 1) {
-        dim3 grid((p.HU + kMcuPerCta - 1) / kMcuPerCta, p.VU, nimg);
-        k_fwd_transform_f64<<<grid, kFwdThreads, 0, st>>>(p);
-    } else {
-        dim3 grid((p.HU + kTileMcu - 1) / kTileMcu, p.VU, nimg);
-        if (ctx->transform_variant == 2) (void)jz_launch(k_fwd_transform_t<false>, grid, dim3(256), 0, st, p);    // one thread per block (A/B runs)
-        else {
-            if (!ctx->fwd_attr_set) {   // static + dynamic shared memory exceed 48 KiB: opt in once per context
-                JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdTrSmem));
-                ctx->fwd_attr_set = true;
-            }
-            (void)jz_launch(k_fwd_transform_t<true>, grid, dim3(256), kFwdTrSmem, st, p);
-        }
-    }
-    ++ctx->launches;
-    JZ_CUDA_TRY(ctx, cudaGetLastError());
-    return JPEZYB200_OK;
+    return launch_fwd_kernel(ctx, p, nimg, st);
 }
 
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -94,7 +94,7 @@ struct jpezyb200_ctx {
     int sync_rounds = 3;
     int64_t group_bytes = int64_t(96) << 20;   // host<->device bytes per stage of the pipelined host batches
     uint64_t launches = 0;
-    bool inv_attr_set = false, fwd_attr_set = false;
+    bool inv_attr_set = false, fwd_attr_set = false, fwd2_attr_set = false;
 
     // device-resident tables
     jz::HuffEncLut* d_enc_lut = nullptr;  // [2]
