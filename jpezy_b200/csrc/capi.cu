@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "dec_entropy.cuh"
 #include "dec_transform.cuh"
+#include "dec_transform2.cuh"
 #include "enc_entropy.cuh"
 #include "enc_transform.cuh"
 #include "enc_transform2.cuh"
@@ -140,9 +141,8 @@ int jpezyb200_ctx_create(int device, jpezyb200_ctx** out)
             JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(gIzzCol, izzc, sizeof izzc));
             // second-generation forward kernel (enc_transform2.cuh): (K, K) pairs per (class, column); the DC multiplier
             // carries 1 - 2^-20 so that trunc(S * K) reproduces int(int(((S*c)*c)/4)/q) for every sum S; class 2 = zeros
-            Q2Col q2[3][8];
-            float g2[2][8][8], thr[3];
-            std::memset(q2, 0, sizeof q2);
+            Q2Tab q2;
+            std::memset(&q2, 0, sizeof q2);
             for (int c = 0; c < 2; ++c) {
                 double gmax = 0.0;
                 for (int j = 0; j < 8; ++j)
@@ -150,15 +150,14 @@ int jpezyb200_ctx_create(int device, jpezyb200_ctx** out)
                         float K = qc.K[c][i * 8 + j];
                         if ((i | j) == 0) K = float((1.0 - 1.0 / 1048576.0) / (8.0 * (c ? kQuantChroma[0] : kQuantLuma[0])));
                         else gmax = std::max(gmax, double(qc.G[c][i * 8 + j]));
-                        q2[c][j].K[i] = make_float2(K, K);
-                        g2[c][j][i] = qc.G[c][i * 8 + j];
+                        q2.K[c][j][i] = make_float2(K, K);
+                        q2.G[c][j][i] = qc.G[c][i * 8 + j];
                     }
-                thr[c] = float(1.0 - 2.0 * gmax);
+                const float thr = float(1.0 - 2.0 * gmax);
+                std::memcpy(&q2.thr[c], &thr, 4);
             }
-            thr[2] = 3.0e38f;
-            JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(gQ2K, q2, sizeof q2));
-            JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(gQ2G, g2, sizeof g2));
-            JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(gQ2Thr, thr, sizeof thr));
+            for (int j = 0; j < 8; ++j) q2.izz[j] = izzc[j];
+            JZ_CUDA_TRY(ctx, cudaMemcpyToSymbol(gQ2, &q2, sizeof q2));
         }
         HuffEncLut lut[2];
         build_enc_lut(kDcLuma, kAcLuma, &lut[0]);
@@ -196,6 +195,8 @@ void jpezyb200_ctx_destroy(jpezyb200_ctx* ctx)
     if (ctx->d_dec_lut) cudaFree(ctx->d_dec_lut);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_y_exact) cudaFree(ctx->d_y_exact);
+    for (void* tb : ctx->inv2_tab)
+        if (tb) cudaFree(tb);
     jz::batch_pipe_destroy(ctx);
     host_pipe_destroy(ctx);
     std::free(ctx->shard_state);
@@ -310,15 +311,29 @@ static int launch_fwd_kernel(jpezyb200_ctx* ctx, const FwdParams& p, uint32_t ni
         dim3 grid((p.HU + kMcuPerCta - 1) / kMcuPerCta, p.VU, nimg);
         k_fwd_transform_f64<<<grid, kFwdThreads, 0, st>>>(p);
     } else if (ctx->transform_variant == 0 && fwd2_ok(p)) {
-        // second-generation kernel: rows fetched by bulk copies, needs 16-byte aligned rows and buffers
-        static const int tile_mcu = [] { const char* e = std::getenv("JPEZY_B200_FWD_TILE"); return e && std::atoi(e) == 16 ? 16 : 8; }();
+        // second-generation kernel: persistent CTAs, rows fetched by bulk copies (needs 16-byte aligned rows and buffers)
+        static const int cfg = [] { const char* e = std::getenv("JPEZY_B200_FWD_CFG"); return e ? std::atoi(e) : 83; }();   // tile MCUs * 10 + stages
         if (!ctx->fwd2_attr_set) {
-            JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2<8>::kSmem));
-            JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2<16>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform2<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2<8, 3>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform2<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2<8, 2>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform2<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2<16, 2>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->fwd2_occ[0], k_fwd_transform2<8, 3>, Fwd2<8, 3>::kThreads, Fwd2<8, 3>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->fwd2_occ[1], k_fwd_transform2<8, 2>, Fwd2<8, 2>::kThreads, Fwd2<8, 2>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->fwd2_occ[2], k_fwd_transform2<16, 2>, Fwd2<16, 2>::kThreads, Fwd2<16, 2>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
             ctx->fwd2_attr_set = true;
         }
-        if (tile_mcu == 16) (void)jz_launch(k_fwd_transform2<16>, dim3((p.HU + 15) / 16, p.VU, nimg), dim3(Fwd2<16>::kThreads), Fwd2<16>::kSmem, st, p);
-        else (void)jz_launch(k_fwd_transform2<8>, dim3((p.HU + 7) / 8, p.VU, nimg), dim3(Fwd2<8>::kThreads), Fwd2<8>::kSmem, st, p);
+        const int T = cfg / 10 == 16 ? 16 : 8, v = T == 16 ? 2 : (cfg % 10 == 2 ? 1 : 0);
+        const uint32_t tpr = (p.HU + T - 1) / T;
+        const uint64_t ntiles64 = uint64_t(tpr) * p.VU * nimg;
+        if (ntiles64 > 0xffffffffull) return ctx->fail(JPEZYB200_EINVAL, "too many tiles");
+        const uint32_t ntiles = uint32_t(ntiles64);
+        static const int per_sm_cap = [] { const char* e = std::getenv("JPEZY_B200_FWD_CTAS"); return e ? std::atoi(e) : 0; }();
+        const int per_sm = per_sm_cap > 0 ? std::min(per_sm_cap, ctx->fwd2_occ[v]) : ctx->fwd2_occ[v];
+        const uint32_t grid = std::min<uint32_t>(ntiles, uint32_t(ctx->num_sms * std::max(1, per_sm)));
+        if (v == 0) (void)jz_launch(k_fwd_transform2<8, 3>, dim3(grid), dim3(Fwd2<8, 3>::kThreads), Fwd2<8, 3>::kSmem, st, p, ntiles, tpr);
+        else if (v == 1) (void)jz_launch(k_fwd_transform2<8, 2>, dim3(grid), dim3(Fwd2<8, 2>::kThreads), Fwd2<8, 2>::kSmem, st, p, ntiles, tpr);
+        else (void)jz_launch(k_fwd_transform2<16, 2>, dim3(grid), dim3(Fwd2<16, 2>::kThreads), Fwd2<16, 2>::kSmem, st, p, ntiles, tpr);
     } else {
         dim3 grid((p.HU + kTileMcu - 1) / kTileMcu, p.VU, nimg);
         if (ctx->transform_variant == 2) (void)jz_launch(k_fwd_transform_t<false>, grid, dim3(256), 0, st, p);    // one thread per block (A/B runs)

@@ -94,7 +94,12 @@ struct jpezyb200_ctx {
     int sync_rounds = 3;
     int64_t group_bytes = int64_t(96) << 20;   // host<->device bytes per stage of the pipelined host batches
     uint64_t launches = 0;
-    bool inv_attr_set = false, fwd_attr_set = false, fwd2_attr_set = false;
+    bool inv_attr_set = false, fwd_attr_set = false, fwd2_attr_set = false, inv2_attr_set = false;
+    int fwd2_occ[3] = {1, 1, 1}, num_sms = 148;   // resident CTAs per SM of the persistent forward kernels, SMs of the device
+    static constexpr int kInv2Slots = 4;       // tables of k_inv_transform2 per set of quantisation tables (capi_decode.inc)
+    void* inv2_tab[kInv2Slots] = {};
+    uint16_t inv2_key[kInv2Slots][3][64] = {};
+    int inv2_next = 0;
 
     // device-resident tables
     jz::HuffEncLut* d_enc_lut = nullptr;  // [2]

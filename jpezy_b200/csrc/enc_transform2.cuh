@@ -83,14 +83,15 @@ __device__ __forceinline__ float fmax3_abs(float a, float b, float c)
 }
 
 // ---- constants of the second-generation kernel --------------------------------------------------------------------
-// per (class, column j): the eight multipliers of coefficients (0..7, j) as (K, K) pairs.  Class 2 is all zero: lanes whose
-// MCU lies beyond the image take it and quantise everything to 0.  K of the DC coefficient carries the factor 1 - 2^-20.
-struct Q2Col {
-    float2 K[8];
+// per (class, column j) the eight multipliers of coefficients (0..7, j) as (K, K) pairs, the guard bands, the zig-zag positions
+struct Q2Tab {
+    float2 K[2][8][8];     // [class][j][i]: (K, K) of coefficient (i, j); K of the DC coefficient carries the factor 1 - 2^-20
+    float G[2][8][8];      // [class][j][i]: guard band in w units
+    uint2 izz[8];          // [j]: zig-zag positions of coefficients (0..7, j), one byte each
+    uint32_t thr[2];       // bit pattern of 1 - 2 Gmax: |w| below it quantises to 0 whatever the coefficient
+    uint32_t pad[2];
 };
-static __device__ Q2Col gQ2K[3][8];
-static __device__ float gQ2G[2][8][8];     // [class][j][i] guard band in w units
-static __device__ float gQ2Thr[3];         // |w| below this for every AC coefficient of a pair: all of them quantise to 0
+static __device__ Q2Tab gQ2;
 
 constexpr float kMagic15 = 12582912.0f;    // 1.5 * 2^23: float(kMagic15 + n) has the integer n in its low mantissa bits (|n| < 2^22)
 constexpr uint32_t kMagic15Bits = 0x4B400000u;
@@ -105,9 +106,12 @@ __device__ __forceinline__ uint32_t mac_byte(int c, uint32_t w, uint32_t acc)
 
 // trunc(n / D) for the two integers held (as floats) in n2, D = 1000 or 10000, RCP = fl(1/D) rounded up; also the residual
 // n - D * trunc(n / D), which is 0 exactly for the multiples of D
-__device__ __forceinline__ f32x2 trunc_div2(f32x2 n2, float rcp, float negd, f32x2& res)
+// (sgn = 0x80000000 and m23 = 0x4B000000 come in registers: with both as immediates the sign transfer is two LOP3, not one)
+__device__ __forceinline__ f32x2 trunc_div2(f32x2 n2, float rcp, float negd, uint32_t sgn, uint32_t m23, f32x2& res)
 {
-    const uint32_t mlo = (uint32_t(n2) & 0x80000000u) | 0x4B000000u, mhi = (uint32_t(n2 >> 32) & 0x80000000u) | 0x4B000000u;
+    uint32_t mlo, mhi;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(mlo) : "r"(uint32_t(n2)), "r"(sgn), "r"(m23));            // (n & sgn) | m23
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(mhi) : "r"(uint32_t(n2 >> 32)), "r"(sgn), "r"(m23));
     const f32x2 m = (unsigned long long)mlo | ((unsigned long long)mhi << 32);      // +-2^23, the sign of n
     const f32x2 q = sub2(fma2_rz(n2, pk2(rcp, rcp), m), m);
     res = fma2(q, pk2(negd, negd), n2);
@@ -178,193 +182,225 @@ __device__ __noinline__ int requant_finish2(double acc, const uint8_t* s_in, uin
     return __double2int_rz(v) / q;
 }
 
-template <int T>
+template <int T, int NST>
 struct Fwd2 {
     static constexpr int kThreads = T * 24;           // one lane per (block pair, row / column): 3 T pairs x 8
     static constexpr int kRow = T * 16 + 16;          // bytes per staged pixel row; == 16 (mod 128): 8-byte reads down a column hit distinct banks
-    static constexpr int kIn = 48 * kRow;
+    static constexpr int kIn = 48 * kRow;             // one input stage: 3 planes x 16 rows
     static constexpr int kPairRow = 80;               // 8 x f32x2 + 16: the lanes' 16-byte row stores land on distinct banks
     static constexpr int kPair = 8 * kPairRow + 64;   // == 64 (mod 128): the two pairs of a half warp read disjoint banks
     static constexpr int kMid = T * 3 * kPair;
-    static constexpr int kOut = T * 768;
+    static constexpr int kOut = T * 768;              // one staging buffer (two of them: a bulk store may still be reading the other)
     static constexpr int kMeta = T * 6 * 4;
-    static constexpr int kSmem = kIn + kMid + kOut + kMeta + kFixCap * 2 + 16;
+    static constexpr int kSmem = NST * kIn + kMid + 2 * kOut + 2 * kMeta + kFixCap * 2 + 16 + NST * 8 + int(sizeof(Q2Tab));
     static_assert(kRow % 128 == 16 && kIn % 16 == 0 && kMid % 16 == 0, "layout");
 };
 
-template <int T>
-__global__ void __launch_bounds__(T * 24, T == 8 ? 5 : 2) k_fwd_transform2(const FwdParams p)
+// Persistent CTAs: CTA b transforms tiles b, b + gridDim.x, ... (a tile = T MCUs of one MCU row of one image).  The pixel rows
+// of tile i + NST - 1 are already in flight (TMA bulk copies into a ring of NST stages, one mbarrier per stage) while tile i is
+// transformed; the coefficients of tile i - 1 leave through a bulk store while tile i fills the other staging buffer.  One
+// CTA-wide barrier per tile (two when the fix-up queue is not empty).
+template <int T, int NST>
+__global__ void __launch_bounds__(T * 24, T == 8 ? 4 : 2) k_fwd_transform2(const FwdParams p, const uint32_t ntiles, const uint32_t tiles_per_row)
 {
-    using C = Fwd2<T>;
+    using C = Fwd2<T, NST>;
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* s_in = smem;                                            // [3 planes][16 rows][kRow]
-    uint8_t* s_mid = s_in + C::kIn;                                  // [3T pairs][8][kPairRow]: row-transformed samples, (A, B) packed
-    int16_t* s_out = reinterpret_cast<int16_t*>(s_mid + C::kMid);    // [6T blocks][64] zig-zag coefficients, scan order
-    uint32_t* s_meta = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_out) + C::kOut);
-    uint16_t* s_fix = reinterpret_cast<uint16_t*>(s_meta + T * 6);
+    uint8_t* s_in0 = smem;                                           // [NST][3 planes][16 rows][kRow]
+    uint8_t* s_mid = s_in0 + NST * C::kIn;                           // [3T pairs][8][kPairRow]: row-transformed samples, (A, B) packed
+    uint8_t* s_out0 = s_mid + C::kMid;                               // [2][6T blocks][64] int16 zig-zag coefficients, scan order
+    Q2Tab* s_tab = reinterpret_cast<Q2Tab*>(s_out0 + 2 * C::kOut);   // quantisation constants (copied once per CTA), 16-byte aligned
+    uint32_t* s_meta0 = reinterpret_cast<uint32_t*>(s_tab + 1);
+    uint16_t* s_fix = reinterpret_cast<uint16_t*>(s_meta0 + 2 * T * 6);
     uint32_t* s_nfix = reinterpret_cast<uint32_t*>(s_fix + kFixCap);
-    const uint32_t bar = smem_u32(s_nfix + 2);
+    const uint32_t bar0 = smem_u32(s_nfix + 4);                      // NST barriers of 8 bytes; s_nfix[0..2]: queue lengths of tiles it % 3
+    static_assert(sizeof(Q2Tab) % 16 == 0 && (2 * T * 6 * 4) % 8 == 0, "alignment of the barriers");
 
     const int t = threadIdx.x, lane = t & 31;
-    const uint32_t mx0 = blockIdx.x * T, my = blockIdx.y;
-    const size_t img = blockIdx.z;
-    const uint32_t nvalid = min(uint32_t(T), p.HU - mx0);
-    const uint32_t gy0 = (p.row0 + my) * 16u;
-    const int hlast = int(min(15u, p.H - 1u - gy0));                  // last staged row; rows below replicate it (:101)
-
-    if (t == 0) {
-        mbar_init(bar, 1);
-        *s_nfix = 0;
-        mbar_fence_init();
-    }
-    {   // the staging buffer starts as zeros: only non-zero coefficients are stored
-        uint4* z = reinterpret_cast<uint4*>(s_out) + t * 2;
-        z[0] = z[1] = make_uint4(0, 0, 0, 0);
-        if (t < T * 6) s_meta[t] = 0;
-    }
-    __syncthreads();
-    pdl_wait();
-    if (t < 32) {
-        const uint32_t rowbytes = nvalid * 16u;
+    const uint32_t tiles_per_img = tiles_per_row * p.VU;
+    // tile id -> image, MCU row, first MCU
+    auto geom = [&](uint32_t id, uint32_t& img, uint32_t& my, uint32_t& mx0) {
+        img = id / tiles_per_img;
+        const uint32_t rem = id - img * tiles_per_img;
+        my = rem / tiles_per_row;
+        mx0 = (rem - my * tiles_per_row) * T;
+    };
+    // warp 0: the bulk copies of tile `id` into stage `st` (one per pixel row and plane)
+    auto issue = [&](uint32_t id, int st) {
+        uint32_t img, my, mx0;
+        geom(id, img, my, mx0);
+        const uint32_t nvalid = min(uint32_t(T), p.HU - mx0), gy0 = (p.row0 + my) * 16u;
+        const int hlast = int(min(15u, p.H - 1u - gy0));
+        const uint32_t rowbytes = nvalid * 16u, bar = bar0 + 8u * st;
         if (lane == 0) mbar_expect_tx(bar, 3u * uint32_t(hlast + 1) * rowbytes);
         __syncwarp();
         for (int c = lane; c < 48; c += 32) {
             const int plane = c >> 4, row = c & 15;
             if (row <= hlast) {
-                const uint8_t* src = (plane == 0 ? p.r : (plane == 1 ? p.g : p.b)) + img * p.plane_stride + size_t(gy0 - p.y_origin + row) * p.W + size_t(mx0) * 16u;
-                bulk_g2s(smem_u32(s_in + c * C::kRow), src, rowbytes, bar);
+                const uint8_t* src = (plane == 0 ? p.r : (plane == 1 ? p.g : p.b)) + size_t(img) * p.plane_stride + size_t(gy0 - p.y_origin + row) * p.W + size_t(mx0) * 16u;
+                bulk_g2s(smem_u32(s_in0 + st * C::kIn + c * C::kRow), src, rowbytes, bar);
             }
+        }
+    };
+
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) mbar_init(bar0 + 8u * s, 1);
+        s_nfix[0] = s_nfix[1] = s_nfix[2] = 0;
+        mbar_fence_init();
+    }
+    for (uint32_t i = t; i < sizeof(Q2Tab) / 4; i += C::kThreads) reinterpret_cast<uint32_t*>(s_tab)[i] = reinterpret_cast<const uint32_t*>(&gQ2)[i];
+    __syncthreads();
+    pdl_wait();
+    if (t < 32) {
+#pragma unroll
+        for (int s = 0; s < NST - 1; ++s) {
+            const uint32_t id = blockIdx.x + s * gridDim.x;
+            if (id < ntiles) issue(id, s);
         }
     }
 
-    // ---- the item of this thread: block pair pr, row / column sub ----
+    // ---- the items of this thread: block pair pr, row (phase 1) / column (phase 2) sub ----
     const uint32_t pr = uint32_t(t) >> 3, sub = uint32_t(t) & 7u;
     const bool luma = pr < 2u * T;                                   // warp uniform (4 pairs per warp)
     const uint32_t mcu = luma ? (pr >> 1) : pr - 2u * T;
-    const bool valid = mcu < nvalid;
     const uint32_t blkA = luma ? mcu * 6u + (pr & 1u) : mcu * 6u + 4u, blkB = luma ? blkA + 2u : blkA + 1u;
     uint8_t* mid = s_mid + pr * C::kPair;
+    const bool work = luma || !p.gray;                               // --gray: Cb = Cr = 0 (:61-64), the chroma blocks are all zero
 
-    mbar_wait(bar, 0);
+    uint32_t sgn_bit, m23_bits;          // kept out of the immediate fields (trunc_div2)
+    asm volatile("mov.u32 %0, 0x80000000;" : "=r"(sgn_bit));
+    asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(m23_bits));
 
-    // ---- phase 1: colour conversion of rows sub and sub + 8 (luma) / row 2 sub (chroma), transform along x ----
-    if (luma || !p.gray) {
-        f32x2 y2[8];
-        if (luma) {
-            const int rowA = min(int(sub), hlast), rowB = min(int(sub) + 8, hlast);
-            const uint32_t col = mcu * 16u + (pr & 1u) * 8u;
-            const uint8_t *pa = s_in + rowA * C::kRow + col, *pb = s_in + rowB * C::kRow + col;
-            const uint2 ra = *reinterpret_cast<const uint2*>(pa), ga = *reinterpret_cast<const uint2*>(pa + 16 * C::kRow), ba = *reinterpret_cast<const uint2*>(pa + 32 * C::kRow);
-            const uint2 rb = *reinterpret_cast<const uint2*>(pb), gb = *reinterpret_cast<const uint2*>(pb + 16 * C::kRow), bb = *reinterpret_cast<const uint2*>(pb + 32 * C::kRow);
-            constexpr uint32_t kInit = kMagic15Bits - 128000u;
-            f32x2 prod = pk2(1.0f, 1.0f);
+    uint32_t it = 0;
+    for (uint32_t id = blockIdx.x; id < ntiles; id += gridDim.x, ++it) {
+        const int st = int(it % NST), ob = int(it & 1u);
+        if (t < 32) {
+            const uint32_t nid = id + (NST - 1) * gridDim.x;        // its stage was last read by tile it - 1 (behind the barrier below)
+            if (nid < ntiles) issue(nid, int((it + NST - 1) % NST));
+        }
+        uint32_t img, my, mx0;
+        geom(id, img, my, mx0);
+        const uint32_t nvalid = min(uint32_t(T), p.HU - mx0);
+        const int hlast = int(min(15u, p.H - 1u - (p.row0 + my) * 16u));   // last staged row; rows below replicate it (:101)
+        const bool valid = mcu < nvalid;
+        const uint8_t* s_in = s_in0 + st * C::kIn;
+        int16_t* s_out = reinterpret_cast<int16_t*>(s_out0 + ob * C::kOut);
+        uint32_t* s_meta = s_meta0 + ob * T * 6;
+        uint32_t* nfix_p = s_nfix + it % 3u;
+        {   // this lane's share of the pair's staging area starts as zeros: only non-zero coefficients are stored (the bulk store
+            // that last read this buffer, two tiles ago, was waited for in front of the previous tile's barrier)
+            reinterpret_cast<uint4*>(s_out + blkA * 64u)[sub] = make_uint4(0, 0, 0, 0);
+            reinterpret_cast<uint4*>(s_out + blkB * 64u)[sub] = make_uint4(0, 0, 0, 0);
+        }
+        mbar_wait(bar0 + 8u * st, (it / NST) & 1u);
+
+        // ---- phase 1: colour conversion of rows sub and sub + 8 (luma) / row 2 sub (chroma), transform along x ----
+        if (work) {
+            f32x2 y2[8];
+            if (luma) {
+                const int rowA = min(int(sub), hlast), rowB = min(int(sub) + 8, hlast);
+                const uint32_t col = mcu * 16u + (pr & 1u) * 8u;
+                const uint8_t *pa = s_in + rowA * C::kRow + col, *pb = s_in + rowB * C::kRow + col;
+                const uint2 ra = *reinterpret_cast<const uint2*>(pa), ga = *reinterpret_cast<const uint2*>(pa + 16 * C::kRow), ba = *reinterpret_cast<const uint2*>(pa + 32 * C::kRow);
+                const uint2 rb = *reinterpret_cast<const uint2*>(pb), gb = *reinterpret_cast<const uint2*>(pb + 16 * C::kRow), bb = *reinterpret_cast<const uint2*>(pb + 32 * C::kRow);
+                constexpr uint32_t kInit = kMagic15Bits - 128000u;
+                f32x2 res[8];
 #pragma unroll
-            for (int x = 0; x < 8; ++x) {
-                uint32_t fa, fb;
+                for (int x = 0; x < 8; ++x) {
+                    uint32_t fa, fb;
 #define JZ_Y_SUM(E, R, G, B) mac_byte<E>(299, R, mac_byte<E>(587, G, mac_byte<E>(114, B, kInit)))
-                switch (x & 3) {
-                case 0: fa = JZ_Y_SUM(0, x < 4 ? ra.x : ra.y, x < 4 ? ga.x : ga.y, x < 4 ? ba.x : ba.y), fb = JZ_Y_SUM(0, x < 4 ? rb.x : rb.y, x < 4 ? gb.x : gb.y, x < 4 ? bb.x : bb.y); break;
-                case 1: fa = JZ_Y_SUM(1, x < 4 ? ra.x : ra.y, x < 4 ? ga.x : ga.y, x < 4 ? ba.x : ba.y), fb = JZ_Y_SUM(1, x < 4 ? rb.x : rb.y, x < 4 ? gb.x : gb.y, x < 4 ? bb.x : bb.y); break;
-                case 2: fa = JZ_Y_SUM(2, x < 4 ? ra.x : ra.y, x < 4 ? ga.x : ga.y, x < 4 ? ba.x : ba.y), fb = JZ_Y_SUM(2, x < 4 ? rb.x : rb.y, x < 4 ? gb.x : gb.y, x < 4 ? bb.x : bb.y); break;
-                default: fa = JZ_Y_SUM(3, x < 4 ? ra.x : ra.y, x < 4 ? ga.x : ga.y, x < 4 ? ba.x : ba.y), fb = JZ_Y_SUM(3, x < 4 ? rb.x : rb.y, x < 4 ? gb.x : gb.y, x < 4 ? bb.x : bb.y); break;
-                }
+                    switch (x & 3) {
+                    case 0: fa = JZ_Y_SUM(0, x < 4 ? ra.x : ra.y, x < 4 ? ga.x : ga.y, x < 4 ? ba.x : ba.y), fb = JZ_Y_SUM(0, x < 4 ? rb.x : rb.y, x < 4 ? gb.x : gb.y, x < 4 ? bb.x : bb.y); break;
+                    case 1: fa = JZ_Y_SUM(1, x < 4 ? ra.x : ra.y, x < 4 ? ga.x : ga.y, x < 4 ? ba.x : ba.y), fb = JZ_Y_SUM(1, x < 4 ? rb.x : rb.y, x < 4 ? gb.x : gb.y, x < 4 ? bb.x : bb.y); break;
+                    case 2: fa = JZ_Y_SUM(2, x < 4 ? ra.x : ra.y, x < 4 ? ga.x : ga.y, x < 4 ? ba.x : ba.y), fb = JZ_Y_SUM(2, x < 4 ? rb.x : rb.y, x < 4 ? gb.x : gb.y, x < 4 ? bb.x : bb.y); break;
+                    default: fa = JZ_Y_SUM(3, x < 4 ? ra.x : ra.y, x < 4 ? ga.x : ga.y, x < 4 ? ba.x : ba.y), fb = JZ_Y_SUM(3, x < 4 ? rb.x : rb.y, x < 4 ? gb.x : gb.y, x < 4 ? bb.x : bb.y); break;
+                    }
 #undef JZ_Y_SUM
-                const f32x2 n2 = sub2((unsigned long long)fa | ((unsigned long long)fb << 32), pk2(kMagic15, kMagic15));
-                f32x2 res;
-                y2[x] = trunc_div2(n2, kRcp1000, -1000.0f, res);
-                prod = mul2(prod, res);
-            }
-            if (lo2(prod) * hi2(prod) == 0.0f) {      // ~1.6 % of the items: a weighted sum is an exact multiple of 1000
-                const uint32_t na = luma_fix_row(pa, pa + 16 * C::kRow, pa + 32 * C::kRow, p.y_exact);
-                const uint32_t nb = luma_fix_row(pb, pb + 16 * C::kRow, pb + 32 * C::kRow, p.y_exact);
-#pragma unroll
-                for (int x = 0; x < 8; ++x) y2[x] = add2(y2[x], pk2(nibble_f(na, x), nibble_f(nb, x)));
-            }
-        } else {
-            const int row = min(2 * int(sub), hlast);
-            const uint8_t* pa = s_in + row * C::kRow + mcu * 16u;
-            const uint4 rv = *reinterpret_cast<const uint4*>(pa), gv = *reinterpret_cast<const uint4*>(pa + 16 * C::kRow), bv = *reinterpret_cast<const uint4*>(pa + 32 * C::kRow);
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
-            f32x2 prod = pk2(1.0f, 1.0f);
-#pragma unroll
-            for (int x = 0; x < 8; ++x) {          // decimation, not averaging (:116-143): the even pixels of the even rows
-                const uint32_t r = rw[x >> 1], g = gw[x >> 1], b = bw[x >> 1];
-                uint32_t fcb, fcr;
-                if (x & 1) {
-                    fcb = mac_byte<2>(-1687, r, mac_byte<2>(-3313, g, mac_byte<2>(5000, b, kMagic15Bits)));
-                    fcr = mac_byte<2>(5000, r, mac_byte<2>(-4187, g, mac_byte<2>(-813, b, kMagic15Bits)));
-                } else {
-                    fcb = mac_byte<0>(-1687, r, mac_byte<0>(-3313, g, mac_byte<0>(5000, b, kMagic15Bits)));
-                    fcr = mac_byte<0>(5000, r, mac_byte<0>(-4187, g, mac_byte<0>(-813, b, kMagic15Bits)));
+                    const f32x2 n2 = sub2((unsigned long long)fa | ((unsigned long long)fb << 32), pk2(kMagic15, kMagic15));
+                    y2[x] = trunc_div2(n2, kRcp1000, -1000.0f, sgn_bit, m23_bits, res[x]);
                 }
-                const f32x2 n2 = sub2((unsigned long long)fcb | ((unsigned long long)fcr << 32), pk2(kMagic15, kMagic15));
-                f32x2 res;
-                y2[x] = trunc_div2(n2, kRcp10000, -10000.0f, res);
-                prod = mul2(prod, res);
-            }
-            if (lo2(prod) * hi2(prod) == 0.0f) {      // exact multiples of 10000 (r == g, ...): the reference's FP64 rounding decides
-                const unsigned long long nn = chroma_fix_row(pa, pa + 16 * C::kRow, pa + 32 * C::kRow);
+                // a weighted sum that is an exact multiple of 1000 (one pixel in a thousand): the reference's own FP64 rounding
+                // decides, the 64 KiB table of k_build_y_exact holds its verdict per (r, g).  One product per lane finds out
+                // whether the warp has such a pixel at all (4 warps in 10 do), one vote per column where.
+                f32x2 prod = mul2(mul2(mul2(res[0], res[1]), mul2(res[2], res[3])), mul2(mul2(res[4], res[5]), mul2(res[6], res[7])));
+                if (__any_sync(0xffffffffu, lo2(prod) * hi2(prod) == 0.0f)) {
 #pragma unroll
-                for (int x = 0; x < 8; ++x) y2[x] = add2(y2[x], pk2(nibble_f(uint32_t(nn), x), nibble_f(uint32_t(nn >> 32), x)));
+                    for (int x = 0; x < 8; ++x) {
+                        const bool za = lo2(res[x]) == 0.0f, zb = hi2(res[x]) == 0.0f;
+                        if (__any_sync(0xffffffffu, za || zb)) {
+                            float ca = 0.0f, cb = 0.0f;       // (the pixel's r and g come from the staged rows again: the words are dead by now)
+                            if (za) ca = float(int(__ldg(p.y_exact + (uint32_t(pa[x]) | (uint32_t(pa[16 * C::kRow + x]) << 8)))));
+                            if (zb) cb = float(int(__ldg(p.y_exact + (uint32_t(pb[x]) | (uint32_t(pb[16 * C::kRow + x]) << 8)))));
+                            y2[x] = add2(y2[x], pk2(ca, cb));
+                        }
+                    }
+                }
+            } else {
+                // chroma: the exact cases (r == g and b - r even, ...) are a few per cent of natural samples, so the formulas are
+                // evaluated the way the reference does, in FP64 (half rate on this part) -- 8 samples per lane, a quarter of the pixels
+                const int row = min(2 * int(sub), hlast);
+                const uint8_t* pa = s_in + row * C::kRow + mcu * 16u;
+                const uint4 rv = *reinterpret_cast<const uint4*>(pa), gv = *reinterpret_cast<const uint4*>(pa + 16 * C::kRow), bv = *reinterpret_cast<const uint4*>(pa + 32 * C::kRow);
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {          // decimation, not averaging (:116-143): the even pixels of the even rows
+                    const int sh = (x & 1) * 16;
+                    const double r = double((rw[x >> 1] >> sh) & 255u), g = double((gw[x >> 1] >> sh) & 255u), b = double((bw[x >> 1] >> sh) & 255u);
+                    const double cb = __fma_rn(0.5000, b, __dsub_rn(-__dmul_rn(0.1687, r), __dmul_rn(0.3313, g)));            // 0.5 * b is exact
+                    const double cr = __dsub_rn(__fma_rn(0.5000, r, -__dmul_rn(0.4187, g)), __dmul_rn(0.0813, b));            // 0.5 * r is exact
+                    y2[x] = pk2(float(__double2int_rz(cb)), float(__double2int_rz(cr)));
+                }
             }
+            aan_fdct8_x2(y2[0], y2[1], y2[2], y2[3], y2[4], y2[5], y2[6], y2[7]);
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(mid + sub * C::kPairRow);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = make_ulonglong2(y2[2 * k], y2[2 * k + 1]);
         }
-        aan_fdct8_x2(y2[0], y2[1], y2[2], y2[3], y2[4], y2[5], y2[6], y2[7]);
-        ulonglong2* dst = reinterpret_cast<ulonglong2*>(mid + sub * C::kPairRow);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dst[k] = make_ulonglong2(y2[2 * k], y2[2 * k + 1]);
-    }
-    __syncwarp();
+        __syncwarp();
 
-    // ---- phase 2: transform along y, quantisation; lane sub holds column sub of both blocks ----
-    if (luma || !p.gray) {
-        const uint32_t j = sub;
-        const int cls = valid ? (luma ? 0 : 1) : 2;
-        f32x2 d[8];
+        // ---- phase 2: transform along y, quantisation; lane sub holds column sub of both blocks ----
+        if (work) {
+            const uint32_t j = sub;
+            const int cls = luma ? 0 : 1;
+            f32x2 d[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = *reinterpret_cast<const f32x2*>(mid + i * C::kPairRow + j * 8);
-        f32x2 w[8];
-        {
-            const ulonglong2* kq = reinterpret_cast<const ulonglong2*>(&gQ2K[cls][j]);
-            const ulonglong2 k0 = __ldg(kq), k1 = __ldg(kq + 1), k2 = __ldg(kq + 2), k3 = __ldg(kq + 3);
-            aan_fdct8_x2(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
-            w[0] = mul2(d[0], k0.x), w[1] = mul2(d[1], k0.y), w[2] = mul2(d[2], k1.x), w[3] = mul2(d[3], k1.y);
-            w[4] = mul2(d[4], k2.x), w[5] = mul2(d[5], k2.y), w[6] = mul2(d[6], k3.x), w[7] = mul2(d[7], k3.y);
-        }
-        const float thr = __ldg(&gQ2Thr[cls]);
-        float mx = fmax3_abs(lo2(w[1]), hi2(w[1]), 0.0f);
-#pragma unroll
-        for (int i = 2; i < 8; ++i) mx = fmax3_abs(lo2(w[i]), hi2(w[i]), mx);
-        const float m0 = j ? fmaxf(fabsf(lo2(w[0])), fabsf(hi2(w[0]))) : 0.0f;
-        const bool act = fmaxf(mx, m0) >= thr;
-        int dcA = 0, dcB = 0;
-        if (j == 0) {
-            dcA = __float2int_rz(lo2(w[0])), dcB = __float2int_rz(hi2(w[0]));
-            s_out[blkA * 64u] = int16_t(dcA), s_out[blkB * 64u] = int16_t(dcB);
-        }
-        uint32_t gm = 0;        // non-zero zig-zag groups: bits 0..7 block A, 8..15 block B
-        if (__any_sync(0xffffffffu, act)) {
-            uint32_t lm = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float a = fmaxf(fabsf(lo2(w[i])), fabsf(hi2(w[i])));
-                lm |= (a >= thr && (i | j) != 0 ? 1u : 0u) << i;
+            for (int i = 0; i < 8; ++i) d[i] = *reinterpret_cast<const f32x2*>(mid + i * C::kPairRow + j * 8);
+            f32x2 w[8];
+            {
+                const ulonglong2* kq = reinterpret_cast<const ulonglong2*>(&s_tab->K[cls][j]);
+                const ulonglong2 k0 = kq[0], k1 = kq[1], k2 = kq[2], k3 = kq[3];
+                aan_fdct8_x2(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
+                w[0] = mul2(d[0], k0.x), w[1] = mul2(d[1], k0.y), w[2] = mul2(d[2], k1.x), w[3] = mul2(d[3], k1.y);
+                w[4] = mul2(d[4], k2.x), w[5] = mul2(d[5], k2.y), w[6] = mul2(d[6], k3.x), w[7] = mul2(d[7], k3.y);
             }
-            const uint32_t wm = __reduce_or_sync(0xffffffffu, lm);
-            const uint2 izz = gIzzCol[j];
-            const float* G = gQ2G[cls & 1][j];
+            int dcA = 0, dcB = 0;
+            if (j == 0) {
+                dcA = __float2int_rz(lo2(w[0])), dcB = __float2int_rz(hi2(w[0]));
+                s_out[blkA * 64u] = int16_t(dcA), s_out[blkB * 64u] = int16_t(dcB);
+            }
+            // rows of coefficients in which some lane of the warp may quantise to a non-zero value: |w| >= 1 - 2 Gmax.  The
+            // larger magnitude of the pair per row, the warp's maximum of its bit pattern (REDUX), one uniform compare.
+            const uint32_t thr = s_tab->thr[cls];
+            uint32_t gm = 0;        // non-zero zig-zag groups: bits 0..7 block A, 8..15 block B
+            const uint2 izz = s_tab->izz[j];
+            const float* G = s_tab->G[cls][j];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (!(wm & (1u << i))) continue;
+                float a = fmaxf(fabsf(lo2(w[i])), fabsf(hi2(w[i])));
+                if (i == 0) a = j ? a : 0.0f;                                   // the DC coefficient went its own way
+                if (__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(a) : 0u) < thr) continue;
                 const uint32_t zz = __byte_perm(i < 4 ? izz.x : izz.y, 0, 0x4440 + (i & 3));
-                const float g = __ldg(G + i);
+                const float g = G[i];
+                const f32x2 mg = pk2(kMagic15, kMagic15);
+                const f32x2 dl = sub2(w[i], sub2(add2(w[i], mg), mg));          // w - rint(w)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float wv = h ? hi2(w[i]) : lo2(w[i]);
+                    const float dv = h ? hi2(dl) : lo2(dl);
                     const uint32_t blk = h ? blkB : blkA;
                     const int q = __float2int_rz(wv);
-                    const float kf = (wv + kMagic15) - kMagic15;           // rint(w)
-                    if ((i | j) != 0) {
-                        if (fabsf(wv - kf) < g && kf != 0.0f && valid) push_fix(s_nfix, s_fix, (blk << 6) | uint32_t(i * 8) | j);
+                    if ((i | j) != 0 && valid) {
+                        if (fabsf(dv) < g && fabsf(wv) > 0.5f) push_fix(nfix_p, s_fix, (blk << 6) | uint32_t(i * 8) | j);
                         if (q != 0) {
                             s_out[blk * 64u + zz] = int16_t(q);
                             gm |= 1u << ((zz >> 3) + 8u * h);
@@ -372,74 +408,80 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 5 : 2) k_fwd_transform2(const
                     }
                 }
             }
-            gm |= __shfl_xor_sync(0xffffffffu, gm, 1);
-            gm |= __shfl_xor_sync(0xffffffffu, gm, 2);
-            gm |= __shfl_xor_sync(0xffffffffu, gm, 4);
+            if (__any_sync(0xffffffffu, gm != 0u)) {
+                gm |= __shfl_xor_sync(0xffffffffu, gm, 1);
+                gm |= __shfl_xor_sync(0xffffffffu, gm, 2);
+                gm |= __shfl_xor_sync(0xffffffffu, gm, 4);
+            }
+            if (j == 0) {
+                s_meta[blkA] = (uint32_t(dcA) & 0xffffu) | ((gm & 0xffu) << 16);
+                s_meta[blkB] = (uint32_t(dcB) & 0xffffu) | ((gm & 0xff00u) << 8);
+            }
+        } else if (sub == 0) {
+            s_meta[blkA] = 0, s_meta[blkB] = 0;
         }
-        if (j == 0) {
-            s_meta[blkA] = (uint32_t(dcA) & 0xffffu) | ((gm & 0xffu) << 16);
-            s_meta[blkB] = (uint32_t(dcB) & 0xffffu) | ((gm & 0xff00u) << 8);
-        }
-    }
-    fence_async_smem();      // the staging buffer is read by the async proxy (bulk store)
-    __syncthreads();
+        fence_async_smem();      // the staging buffer is read by the async proxy (bulk store)
+        if (t == 0) bulk_wait_read0();      // the previous tile's store has read the other staging buffer: the next tile may fill it
+        __syncthreads();
+        if (t == 0) s_nfix[(it + 2u) % 3u] = 0;      // the previous tile's queue length: read by everyone before this barrier, used again by tile it + 2
 
-    // ---- phase 2b: dense FP64 re-evaluation of the guard-band queue ----
-    {
-        const uint32_t nfix = *s_nfix;
-        if (nfix) {
-            if (nfix > kFixCap) {
-                // queue overflow (adversarial content): every AC coefficient of the tile is re-evaluated
-                for (uint32_t e = t; e < nvalid * 6u * 64u; e += C::kThreads) {
-                    const uint32_t blk = e >> 6, ij = e & 63u, i = ij >> 3, j = ij & 7u;
-                    if (ij == 0 || (p.gray && blk % 6u >= 4u)) continue;
-                    double acc = 0.0;
-                    for (int y = 0; y < 8; ++y) {
-                        double row = 0.0;
-                        for (int x = 0; x < 8; ++x) row = fma(double(tile_sample<C::kRow>(s_in, blk, y, x, hlast, p.gray)), cC.cos_ref[j * 8 + x], row);
-                        acc = fma(row, cC.cos_ref[i * 8 + y], acc);
-                    }
-                    const int q = cC.quant[(blk % 6u) >= 4u][ij];
-                    const int v = requant_finish2<C::kRow>(acc, s_in, blk, int(i), int(j), q, hlast, p.gray, p.guard_counter);
-                    s_out[blk * 64u + cC.izz[ij]] = int16_t(v);
-                    if (v) atomicOr(&s_meta[blk], 1u << (16 + (cC.izz[ij] >> 3)));
-                }
-            } else {
-                // eight lanes per entry: lane s evaluates row s of the separable sum, a 3-step butterfly adds the rows
-                const uint32_t s = uint32_t(t) & 7u;
-                for (uint32_t e0 = 0; e0 < nfix; e0 += C::kThreads / 8) {
-                    const uint32_t e = e0 + (uint32_t(t) >> 3);
-                    const bool actv = e < nfix;
-                    const uint32_t ent = actv ? uint32_t(s_fix[e]) : 0u;
-                    const uint32_t blk = ent >> 6, ij = ent & 63u, i = ij >> 3, j = ij & 7u;
-                    const double* cj = &gCosRef[j * 8];
-                    double row = 0.0;
-#pragma unroll 1
-                    for (int x = 0; x < 8; ++x) row = fma(double(tile_sample<C::kRow>(s_in, blk, int(s), x, hlast, p.gray)), cj[x], row);
-                    double part = row * gCosRef[i * 8 + s];
-                    part += __shfl_xor_sync(0xffffffffu, part, 1);
-                    part += __shfl_xor_sync(0xffffffffu, part, 2);
-                    part += __shfl_xor_sync(0xffffffffu, part, 4);
-                    if (actv && s == 0) {
+        // ---- phase 2b: dense FP64 re-evaluation of the guard-band queue ----
+        {
+            const uint32_t nfix = *nfix_p;
+            if (nfix) {
+                if (nfix > kFixCap) {
+                    // queue overflow (adversarial content): every AC coefficient of the tile is re-evaluated
+                    for (uint32_t e = t; e < nvalid * 6u * 64u; e += C::kThreads) {
+                        const uint32_t blk = e >> 6, ij = e & 63u, i = ij >> 3, j = ij & 7u;
+                        if (ij == 0 || (p.gray && blk % 6u >= 4u)) continue;
+                        double acc = 0.0;
+                        for (int y = 0; y < 8; ++y) {
+                            double row = 0.0;
+                            for (int x = 0; x < 8; ++x) row = fma(double(tile_sample<C::kRow>(s_in, blk, y, x, hlast, p.gray)), cC.cos_ref[j * 8 + x], row);
+                            acc = fma(row, cC.cos_ref[i * 8 + y], acc);
+                        }
                         const int q = cC.quant[(blk % 6u) >= 4u][ij];
-                        const int v = requant_finish2<C::kRow>(part, s_in, blk, int(i), int(j), q, hlast, p.gray, p.guard_counter);
+                        const int v = requant_finish2<C::kRow>(acc, s_in, blk, int(i), int(j), q, hlast, p.gray, p.guard_counter);
                         s_out[blk * 64u + cC.izz[ij]] = int16_t(v);
                         if (v) atomicOr(&s_meta[blk], 1u << (16 + (cC.izz[ij] >> 3)));
                     }
+                } else {
+                    // eight lanes per entry: lane s evaluates row s of the separable sum, a 3-step butterfly adds the rows
+                    const uint32_t s = uint32_t(t) & 7u;
+                    for (uint32_t e0 = 0; e0 < nfix; e0 += C::kThreads / 8) {
+                        const uint32_t e = e0 + (uint32_t(t) >> 3);
+                        const bool actv = e < nfix;
+                        const uint32_t ent = actv ? uint32_t(s_fix[e]) : 0u;
+                        const uint32_t blk = ent >> 6, ij = ent & 63u, i = ij >> 3, j = ij & 7u;
+                        const double* cj = &gCosRef[j * 8];
+                        double row = 0.0;
+#pragma unroll 1
+                        for (int x = 0; x < 8; ++x) row = fma(double(tile_sample<C::kRow>(s_in, blk, int(s), x, hlast, p.gray)), cj[x], row);
+                        double part = row * gCosRef[i * 8 + s];
+                        part += __shfl_xor_sync(0xffffffffu, part, 1);
+                        part += __shfl_xor_sync(0xffffffffu, part, 2);
+                        part += __shfl_xor_sync(0xffffffffu, part, 4);
+                        if (actv && s == 0) {
+                            const int q = cC.quant[(blk % 6u) >= 4u][ij];
+                            const int v = requant_finish2<C::kRow>(part, s_in, blk, int(i), int(j), q, hlast, p.gray, p.guard_counter);
+                            s_out[blk * 64u + cC.izz[ij]] = int16_t(v);
+                            if (v) atomicOr(&s_meta[blk], 1u << (16 + (cC.izz[ij] >> 3)));
+                        }
+                    }
                 }
+                fence_async_smem();
+                __syncthreads();
             }
-            fence_async_smem();
-            __syncthreads();
         }
-    }
 
-    // ---- phase 3: one bulk store of the tile's coefficients (scan order), side information by plain stores ----
-    const size_t mcu0 = size_t(my) * p.HU + mx0;
-    if (t == 0) {
-        bulk_s2g(p.coefs + img * p.coef_stride + mcu0 * 384, smem_u32(s_out), nvalid * 768u);
-        bulk_commit();
+        // ---- phase 3: one bulk store of the tile's coefficients (scan order), side information by plain stores ----
+        const size_t mcu0 = size_t(my) * p.HU + mx0;
+        if (t == 0) {
+            bulk_s2g(p.coefs + size_t(img) * p.coef_stride + mcu0 * 384, smem_u32(s_out), nvalid * 768u);
+            bulk_commit();
+        }
+        if (p.bmeta && uint32_t(t) < nvalid * 6u) p.bmeta[size_t(img) * (p.coef_stride >> 6) + mcu0 * 6 + t] = s_meta[t];
     }
-    if (p.bmeta && uint32_t(t) < nvalid * 6u) p.bmeta[img * (p.coef_stride >> 6) + mcu0 * 6 + t] = s_meta[t];
     if (t == 0) bulk_wait_read0();
 }
 
