@@ -331,9 +331,16 @@ static int launch_fwd_kernel(jpezyb200_ctx* ctx, const FwdParams& p, uint32_t ni
         static const int per_sm_cap = [] { const char* e = std::getenv("JPEZY_B200_FWD_CTAS"); return e ? std::atoi(e) : 0; }();
         const int per_sm = per_sm_cap > 0 ? std::min(per_sm_cap, ctx->fwd2_occ[v]) : ctx->fwd2_occ[v];
         const uint32_t grid = std::min<uint32_t>(ntiles, uint32_t(ctx->num_sms * std::max(1, per_sm)));
-        if (v == 0) (void)jz_launch(k_fwd_transform2<8, 3>, dim3(grid), dim3(Fwd2<8, 3>::kThreads), Fwd2<8, 3>::kSmem, st, p, ntiles, tpr);
-        else if (v == 1) (void)jz_launch(k_fwd_transform2<8, 2>, dim3(grid), dim3(Fwd2<8, 2>::kThreads), Fwd2<8, 2>::kSmem, st, p, ntiles, tpr);
-        else (void)jz_launch(k_fwd_transform2<16, 2>, dim3(grid), dim3(Fwd2<16, 2>::kThreads), Fwd2<16, 2>::kSmem, st, p, ntiles, tpr);
+        // how (image, MCU row, tile of the row) advance when the tile id grows by the grid size
+        TileStep ts{};
+        ts.tiles_per_row = tpr;
+        const uint32_t per_img = tpr * p.VU;
+        ts.dimg = grid / per_img;
+        ts.dmy = (grid % per_img) / tpr;
+        ts.dbx = (grid % per_img) % tpr;
+        if (v == 0) (void)jz_launch(k_fwd_transform2<8, 3>, dim3(grid), dim3(Fwd2<8, 3>::kThreads), Fwd2<8, 3>::kSmem, st, p, ntiles, ts);
+        else if (v == 1) (void)jz_launch(k_fwd_transform2<8, 2>, dim3(grid), dim3(Fwd2<8, 2>::kThreads), Fwd2<8, 2>::kSmem, st, p, ntiles, ts);
+        else (void)jz_launch(k_fwd_transform2<16, 2>, dim3(grid), dim3(Fwd2<16, 2>::kThreads), Fwd2<16, 2>::kSmem, st, p, ntiles, ts);
     } else {
         dim3 grid((p.HU + kTileMcu - 1) / kTileMcu, p.VU, nimg);
         if (ctx->transform_variant == 2) (void)jz_launch(k_fwd_transform_t<false>, grid, dim3(256), 0, st, p);    // one thread per block (A/B runs)

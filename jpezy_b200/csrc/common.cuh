@@ -61,6 +61,14 @@ struct HuffEncLut {
 };
 
 
+// 32-bit load through a shared-space address (no generic-address arithmetic)
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 // number of 16x16 MCUs along one dimension
 __host__ __device__ inline uint32_t mcu_units(uint32_t n) { return (n + 15u) >> 4; }
 

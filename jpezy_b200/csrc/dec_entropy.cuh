@@ -179,12 +179,7 @@ __device__ __noinline__ uint32_t huff_lookup_slow(const HuffSlow* __restrict__ t
 //  * shared memory is addressed with 32-bit shared-space addresses (no generic-address arithmetic in the loop);
 //  * the next symbol comes from the AC table of the block's class or, if this symbol closes the block, from the DC table
 //    of the next block's class: both words are fetched as soon as the window is known, the block-end test selects.
-__device__ __forceinline__ uint32_t lds32(uint32_t saddr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return v;
-}
+// (lds32: common.cuh)
 struct FastBits {
     uint32_t wa;         // shared address of the word after nx
     uint32_t hi, lo, nx; // window words i, i + 1 and the pre-loaded word i + 2

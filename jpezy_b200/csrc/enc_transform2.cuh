@@ -182,127 +182,242 @@ __device__ __noinline__ int requant_finish2(double acc, const uint8_t* s_in, uin
     return __double2int_rz(v) / q;
 }
 
+// ---- shared-memory accesses through 32-bit shared-space addresses (the generic-pointer forms cost 64-bit address arithmetic) ----
+__device__ __forceinline__ uint2 lds64(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ f32x2 lds64x(uint32_t a)
+{
+    f32x2 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128x(uint32_t a, f32x2 lo, f32x2 hi) { asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a), "l"(lo), "l"(hi) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(short(v)) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+// wait with a watchdog: a protocol error must trap, not hang the device
+__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity)
+{
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// exact sample (level-shifted Y, Cb or Cr) at (y, x) of block `blk` (scan order within the tile) from the staged pixels
+template <int ROW>
+__device__ __forceinline__ int tile_sample_s(uint32_t s_in, uint32_t blk, int y, int x, int hlast, int gray)
+{
+    const uint32_t m = blk / 6u, k = blk - m * 6u;
+    int py, px;
+    if (k < 4u) py = int(k >> 1) * 8 + y, px = int(m) * 16 + int(k & 1u) * 8 + x;
+    else py = 2 * y, px = int(m) * 16 + 2 * x;
+    py = min(py, hlast);
+    const uint32_t a = s_in + py * ROW + px;
+    const int r = int(lds8(a)), g = int(lds8(a + 16 * ROW)), b = int(lds8(a + 32 * ROW));
+    if (k < 4u) return fast_Y(r, g, b);
+    if (gray) return 0;
+    return k == 4u ? fast_Cb(r, g, b) : fast_Cr(r, g, b);
+}
+// tier 2 / tier 3 decision on the FP64 separable sum `acc` of coefficient (i, j) of block blk (requant_finish of the
+// first-generation kernel, samples re-derived from the staged pixels)
+template <int ROW>
+__device__ __noinline__ int requant_finish_s(double acc, uint32_t s_in, uint32_t blk, int i, int j, int q, int hlast, int gray, unsigned long long* counter)
+{
+    double v = acc * 0.25 * (i ? 1.0 : 0.70710678118654752440) * (j ? 1.0 : 0.70710678118654752440);
+    const double k = rint(v / double(q));
+    if (k != 0.0 && fabs(v - k * double(q)) < 1e-9) {
+        double sum = 0.0;
+        for (int y = 0; y < 8; ++y) {
+            const double ci = cC.cos_ref[i * 8 + y];
+            for (int x = 0; x < 8; ++x)
+                sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(double(tile_sample_s<ROW>(s_in, blk, y, x, hlast, gray)), cC.cos_ref[j * 8 + x]), ci));
+        }
+        const double cu = j ? 1.0 : cC.inv_sqrt2_ref, cv = i ? 1.0 : cC.inv_sqrt2_ref;
+        v = __dmul_rn(__dmul_rn(__dmul_rn(sum, cu), cv), 0.25);
+        atomicAdd(counter, 1ull);
+    }
+    return __double2int_rz(v) / q;
+}
+
+// per-warp fix-up queue: (block, natural index) entries of 16 bits, length in its own word
+__device__ __noinline__ void push_fix_w(uint32_t a_cnt, uint32_t a_fix, uint32_t blk_ij)
+{
+    uint32_t idx;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(idx) : "r"(a_cnt) : "memory");
+    if (idx < 96u) asm volatile("st.shared.u16 [%0], %1;" ::"r"(a_fix + 2u * idx), "h"(short(blk_ij)) : "memory");
+}
+
+constexpr int kWarpFix = 96;       // fix-up queue entries per compute warp and tile (more: the warp re-evaluates all of its blocks)
+
 template <int T, int NST>
 struct Fwd2 {
-    static constexpr int kThreads = T * 24;           // one lane per (block pair, row / column): 3 T pairs x 8
+    static constexpr int kWarps = T * 24 / 32;        // compute warps: one lane per (block pair, row / column), 4 pairs per warp
+    static constexpr int kThreads = T * 24 + 32;      // + the DMA warp
     static constexpr int kRow = T * 16 + 16;          // bytes per staged pixel row; == 16 (mod 128): 8-byte reads down a column hit distinct banks
     static constexpr int kIn = 48 * kRow;             // one input stage: 3 planes x 16 rows
     static constexpr int kPairRow = 80;               // 8 x f32x2 + 16: the lanes' 16-byte row stores land on distinct banks
     static constexpr int kPair = 8 * kPairRow + 64;   // == 64 (mod 128): the two pairs of a half warp read disjoint banks
-    static constexpr int kMid = T * 3 * kPair;
     static constexpr int kOut = T * 768;              // one staging buffer (two of them: a bulk store may still be reading the other)
-    static constexpr int kMeta = T * 6 * 4;
-    static constexpr int kSmem = NST * kIn + kMid + 2 * kOut + 2 * kMeta + kFixCap * 2 + 16 + NST * 8 + int(sizeof(Q2Tab));
-    static_assert(kRow % 128 == 16 && kIn % 16 == 0 && kMid % 16 == 0, "layout");
+    static constexpr uint32_t oIn = 0, oMid = oIn + NST * kIn, oOut = oMid + T * 3 * kPair, oTab = oOut + 2 * kOut;
+    static constexpr uint32_t oFix = oTab + uint32_t(sizeof(Q2Tab)), oCnt = oFix + kWarps * kWarpFix * 2, oBar = oCnt + 64;
+    static constexpr int kSmem = int(oBar) + (2 * NST + 4) * 8;
+    static_assert(kRow % 128 == 16 && kIn % 16 == 0 && oOut % 16 == 0 && oTab % 16 == 0 && sizeof(Q2Tab) % 16 == 0 && oBar % 8 == 0 && kWarps <= 16, "layout");
 };
 
-// Persistent CTAs: CTA b transforms tiles b, b + gridDim.x, ... (a tile = T MCUs of one MCU row of one image).  The pixel rows
-// of tile i + NST - 1 are already in flight (TMA bulk copies into a ring of NST stages, one mbarrier per stage) while tile i is
-// transformed; the coefficients of tile i - 1 leave through a bulk store while tile i fills the other staging buffer.  One
-// CTA-wide barrier per tile (two when the fix-up queue is not empty).
+// How the tile ids advance from one tile of a CTA to its next (id += gridDim.x), precomputed on the host: no divisions in the loop
+struct TileStep {
+    uint32_t tiles_per_row, dimg, dmy, dbx;
+};
+
+// Persistent, warp-specialised CTAs.  CTA b transforms tiles b, b + gridDim.x, ... (a tile = T MCUs of one MCU row of one image).
+//  * the DMA warp (one lane) keeps NST - 1 tiles of pixel rows in flight (TMA bulk copies into a ring of NST stages, `in_full`
+//    barriers) and sends every finished tile's coefficients off with one bulk store (`out_full` / `out_empty`);
+//  * the compute warps never meet at a CTA barrier: a warp owns its four block pairs from the pixels to the coefficients and to its
+//    own fix-up queue; it tells the DMA warp through `in_empty` / `out_full` when it is done with a stage / a staging buffer.
 template <int T, int NST>
-__global__ void __launch_bounds__(T * 24, T == 8 ? 4 : 2) k_fwd_transform2(const FwdParams p, const uint32_t ntiles, const uint32_t tiles_per_row)
+__global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(const FwdParams p, const uint32_t ntiles, const TileStep ts)
 {
     using C = Fwd2<T, NST>;
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* s_in0 = smem;                                           // [NST][3 planes][16 rows][kRow]
-    uint8_t* s_mid = s_in0 + NST * C::kIn;                           // [3T pairs][8][kPairRow]: row-transformed samples, (A, B) packed
-    uint8_t* s_out0 = s_mid + C::kMid;                               // [2][6T blocks][64] int16 zig-zag coefficients, scan order
-    Q2Tab* s_tab = reinterpret_cast<Q2Tab*>(s_out0 + 2 * C::kOut);   // quantisation constants (copied once per CTA), 16-byte aligned
-    uint32_t* s_meta0 = reinterpret_cast<uint32_t*>(s_tab + 1);
-    uint16_t* s_fix = reinterpret_cast<uint16_t*>(s_meta0 + 2 * T * 6);
-    uint32_t* s_nfix = reinterpret_cast<uint32_t*>(s_fix + kFixCap);
-    const uint32_t bar0 = smem_u32(s_nfix + 4);                      // NST barriers of 8 bytes; s_nfix[0..2]: queue lengths of tiles it % 3
-    static_assert(sizeof(Q2Tab) % 16 == 0 && (2 * T * 6 * 4) % 8 == 0, "alignment of the barriers");
-
-    const int t = threadIdx.x, lane = t & 31;
-    const uint32_t tiles_per_img = tiles_per_row * p.VU;
-    // tile id -> image, MCU row, first MCU
-    auto geom = [&](uint32_t id, uint32_t& img, uint32_t& my, uint32_t& mx0) {
-        img = id / tiles_per_img;
-        const uint32_t rem = id - img * tiles_per_img;
-        my = rem / tiles_per_row;
-        mx0 = (rem - my * tiles_per_row) * T;
-    };
-    // warp 0: the bulk copies of tile `id` into stage `st` (one per pixel row and plane)
-    auto issue = [&](uint32_t id, int st) {
-        uint32_t img, my, mx0;
-        geom(id, img, my, mx0);
-        const uint32_t nvalid = min(uint32_t(T), p.HU - mx0), gy0 = (p.row0 + my) * 16u;
-        const int hlast = int(min(15u, p.H - 1u - gy0));
-        const uint32_t rowbytes = nvalid * 16u, bar = bar0 + 8u * st;
-        if (lane == 0) mbar_expect_tx(bar, 3u * uint32_t(hlast + 1) * rowbytes);
-        __syncwarp();
-        for (int c = lane; c < 48; c += 32) {
-            const int plane = c >> 4, row = c & 15;
-            if (row <= hlast) {
-                const uint8_t* src = (plane == 0 ? p.r : (plane == 1 ? p.g : p.b)) + size_t(img) * p.plane_stride + size_t(gy0 - p.y_origin + row) * p.W + size_t(mx0) * 16u;
-                bulk_g2s(smem_u32(s_in0 + st * C::kIn + c * C::kRow), src, rowbytes, bar);
-            }
-        }
-    };
+    const uint32_t sm = smem_u32(smem);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t bar_in_full = sm + C::oBar, bar_in_empty = bar_in_full + 8u * NST, bar_out_full = bar_in_empty + 8u * NST, bar_out_empty = bar_out_full + 16u;
 
     if (t == 0) {
 #pragma unroll
-        for (int s = 0; s < NST; ++s) mbar_init(bar0 + 8u * s, 1);
-        s_nfix[0] = s_nfix[1] = s_nfix[2] = 0;
+        for (int s = 0; s < NST; ++s) mbar_init(bar_in_full + 8u * s, 1), mbar_init(bar_in_empty + 8u * s, C::kWarps);
+        mbar_init(bar_out_full, C::kWarps), mbar_init(bar_out_full + 8u, C::kWarps);
+        mbar_init(bar_out_empty, 1), mbar_init(bar_out_empty + 8u, 1);
         mbar_fence_init();
     }
-    for (uint32_t i = t; i < sizeof(Q2Tab) / 4; i += C::kThreads) reinterpret_cast<uint32_t*>(s_tab)[i] = reinterpret_cast<const uint32_t*>(&gQ2)[i];
+    for (uint32_t i = t; i < sizeof(Q2Tab) / 4; i += C::kThreads) sts32(sm + C::oTab + 4u * i, reinterpret_cast<const uint32_t*>(&gQ2)[i]);
+    if (t < 16) sts32(sm + C::oCnt + 4u * t, 0u);
     __syncthreads();
     pdl_wait();
-    if (t < 32) {
-#pragma unroll
-        for (int s = 0; s < NST - 1; ++s) {
-            const uint32_t id = blockIdx.x + s * gridDim.x;
-            if (id < ntiles) issue(id, s);
+
+    // tile id -> image, MCU row, tile of the row (divisions once per thread; the loops advance by ts)
+    uint32_t img, my, bx;
+    {
+        const uint32_t per_img = ts.tiles_per_row * p.VU;
+        img = blockIdx.x / per_img;
+        const uint32_t rem = blockIdx.x - img * per_img;
+        my = rem / ts.tiles_per_row, bx = rem - my * ts.tiles_per_row;
+    }
+    auto advance = [&](uint32_t& im, uint32_t& y, uint32_t& x) {
+        x += ts.dbx;
+        if (x >= ts.tiles_per_row) x -= ts.tiles_per_row, ++y;
+        y += ts.dmy;
+        if (y >= p.VU) y -= p.VU, ++im;
+        im += ts.dimg;
+    };
+
+    if (warp == C::kWarps) {
+        // ================= DMA warp =================
+        if (lane != 0) return;
+        uint32_t limg = img, lmy = my, lbx = bx;       // next tile to load
+        uint32_t lid = blockIdx.x;
+        auto issue = [&](int st) {
+            const uint32_t mx0 = lbx * T, nvalid = min(uint32_t(T), p.HU - mx0), gy0 = (p.row0 + lmy) * 16u;
+            const uint32_t nrow = min(16u, p.H - gy0), rowbytes = nvalid * 16u, bar = bar_in_full + 8u * st;
+            mbar_expect_tx(bar, 3u * nrow * rowbytes);
+            const size_t off = size_t(limg) * p.plane_stride + size_t(gy0 - p.y_origin) * p.W + size_t(mx0) * 16u;
+            const uint32_t dst = sm + C::oIn + st * C::kIn;
+#pragma unroll 1
+            for (uint32_t row = 0; row < nrow; ++row) {
+                bulk_g2s(dst + row * C::kRow, p.r + off + size_t(row) * p.W, rowbytes, bar);
+                bulk_g2s(dst + (16 + row) * C::kRow, p.g + off + size_t(row) * p.W, rowbytes, bar);
+                bulk_g2s(dst + (32 + row) * C::kRow, p.b + off + size_t(row) * p.W, rowbytes, bar);
+            }
+            advance(limg, lmy, lbx);
+            lid += gridDim.x;
+        };
+#pragma unroll 1
+        for (int s = 0; s < NST - 1 && lid < ntiles; ++s) issue(s);
+        uint32_t i = 0;
+        int lst = NST - 1;          // stage of the next load
+#pragma unroll 1
+        for (uint32_t id = blockIdx.x; id < ntiles; id += gridDim.x, ++i) {
+            if (lid < ntiles) {
+                // tile i + NST - 1 goes where tile i - 1 was: wait until every compute warp is done with it
+                if (i >= 1) mbar_wait_wd(bar_in_empty + 8u * lst, ((i - 1) / NST) & 1u);
+                issue(lst);
+                lst = lst + 1 == NST ? 0 : lst + 1;
+            }
+            const uint32_t ob = i & 1u;
+            mbar_wait_wd(bar_out_full + 8u * ob, (i >> 1) & 1u);
+            const uint32_t mx0 = bx * T, nvalid = min(uint32_t(T), p.HU - mx0);
+            bulk_s2g(p.coefs + size_t(img) * p.coef_stride + (size_t(my) * p.HU + mx0) * 384, sm + C::oOut + ob * C::kOut, nvalid * 768u);
+            bulk_commit();
+            if (i >= 1) {
+                bulk_wait_read1();                       // the previous tile's store has read its staging buffer
+                mbar_arrive(bar_out_empty + 8u * (ob ^ 1u));
+            }
+            advance(img, my, bx);
         }
+        bulk_wait_read0();
+        return;
     }
 
-    // ---- the items of this thread: block pair pr, row (phase 1) / column (phase 2) sub ----
-    const uint32_t pr = uint32_t(t) >> 3, sub = uint32_t(t) & 7u;
+    // ================= compute warps =================
+    const uint32_t pr = uint32_t(t) >> 3, sub = uint32_t(t) & 7u;    // block pair, row (phase 1) / column (phase 2)
     const bool luma = pr < 2u * T;                                   // warp uniform (4 pairs per warp)
     const uint32_t mcu = luma ? (pr >> 1) : pr - 2u * T;
-    const uint32_t blkA = luma ? mcu * 6u + (pr & 1u) : mcu * 6u + 4u, blkB = luma ? blkA + 2u : blkA + 1u;
-    uint8_t* mid = s_mid + pr * C::kPair;
+    const uint32_t blkA = luma ? mcu * 6u + (pr & 1u) : mcu * 6u + 4u;
+    const uint32_t dAB = luma ? 256u : 128u;                         // block B = Y2 / Y3 / Cr: bytes behind block A
+    const uint32_t a_mid = sm + C::oMid + pr * C::kPair;
     const bool work = luma || !p.gray;                               // --gray: Cb = Cr = 0 (:61-64), the chroma blocks are all zero
-
+    const uint32_t a_fix = sm + C::oFix + warp * (kWarpFix * 2), a_cnt = sm + C::oCnt + 4u * warp;
+    const uint32_t a_tab = sm + C::oTab;
+    const int cls = luma ? 0 : 1;
     uint32_t sgn_bit, m23_bits;          // kept out of the immediate fields (trunc_div2)
     asm volatile("mov.u32 %0, 0x80000000;" : "=r"(sgn_bit));
     asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(m23_bits));
 
-    uint32_t it = 0;
-    for (uint32_t id = blockIdx.x; id < ntiles; id += gridDim.x, ++it) {
-        const int st = int(it % NST), ob = int(it & 1u);
-        if (t < 32) {
-            const uint32_t nid = id + (NST - 1) * gridDim.x;        // its stage was last read by tile it - 1 (behind the barrier below)
-            if (nid < ntiles) issue(nid, int((it + NST - 1) % NST));
-        }
-        uint32_t img, my, mx0;
-        geom(id, img, my, mx0);
-        const uint32_t nvalid = min(uint32_t(T), p.HU - mx0);
+    uint32_t st = 0, stpar = 0, i = 0;
+#pragma unroll 1
+    for (uint32_t id = blockIdx.x; id < ntiles; id += gridDim.x, ++i) {
+        const uint32_t ob = i & 1u;
+        const uint32_t mx0 = bx * T, nvalid = min(uint32_t(T), p.HU - mx0);
         const int hlast = int(min(15u, p.H - 1u - (p.row0 + my) * 16u));   // last staged row; rows below replicate it (:101)
         const bool valid = mcu < nvalid;
-        const uint8_t* s_in = s_in0 + st * C::kIn;
-        int16_t* s_out = reinterpret_cast<int16_t*>(s_out0 + ob * C::kOut);
-        uint32_t* s_meta = s_meta0 + ob * T * 6;
-        uint32_t* nfix_p = s_nfix + it % 3u;
-        {   // this lane's share of the pair's staging area starts as zeros: only non-zero coefficients are stored (the bulk store
-            // that last read this buffer, two tiles ago, was waited for in front of the previous tile's barrier)
-            reinterpret_cast<uint4*>(s_out + blkA * 64u)[sub] = make_uint4(0, 0, 0, 0);
-            reinterpret_cast<uint4*>(s_out + blkB * 64u)[sub] = make_uint4(0, 0, 0, 0);
-        }
-        mbar_wait(bar0 + 8u * st, (it / NST) & 1u);
+        const uint32_t a_in = sm + C::oIn + st * C::kIn;
+        const uint32_t a_outA = sm + C::oOut + ob * C::kOut + blkA * 128u;
+        if (i >= 2) mbar_wait_wd(bar_out_empty + 8u * ob, ((i >> 1) - 1u) & 1u);    // the store of tile i - 2 has read this buffer
+        // this lane's share of the pair's staging area starts as zeros: only non-zero coefficients are stored
+        sts128(a_outA + sub * 16u, 0, 0, 0, 0);
+        sts128(a_outA + dAB + sub * 16u, 0, 0, 0, 0);
+        mbar_wait_wd(bar_in_full + 8u * st, stpar);
 
         // ---- phase 1: colour conversion of rows sub and sub + 8 (luma) / row 2 sub (chroma), transform along x ----
         if (work) {
             f32x2 y2[8];
             if (luma) {
-                const int rowA = min(int(sub), hlast), rowB = min(int(sub) + 8, hlast);
                 const uint32_t col = mcu * 16u + (pr & 1u) * 8u;
-                const uint8_t *pa = s_in + rowA * C::kRow + col, *pb = s_in + rowB * C::kRow + col;
-                const uint2 ra = *reinterpret_cast<const uint2*>(pa), ga = *reinterpret_cast<const uint2*>(pa + 16 * C::kRow), ba = *reinterpret_cast<const uint2*>(pa + 32 * C::kRow);
-                const uint2 rb = *reinterpret_cast<const uint2*>(pb), gb = *reinterpret_cast<const uint2*>(pb + 16 * C::kRow), bb = *reinterpret_cast<const uint2*>(pb + 32 * C::kRow);
+                const uint32_t pa = a_in + min(int(sub), hlast) * C::kRow + col, pb = a_in + min(int(sub) + 8, hlast) * C::kRow + col;
+                const uint2 ra = lds64(pa), ga = lds64(pa + 16 * C::kRow), ba = lds64(pa + 32 * C::kRow);
+                const uint2 rb = lds64(pb), gb = lds64(pb + 16 * C::kRow), bb = lds64(pb + 32 * C::kRow);
                 constexpr uint32_t kInit = kMagic15Bits - 128000u;
                 f32x2 res[8];
 #pragma unroll
@@ -322,15 +437,15 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 4 : 2) k_fwd_transform2(const
                 // a weighted sum that is an exact multiple of 1000 (one pixel in a thousand): the reference's own FP64 rounding
                 // decides, the 64 KiB table of k_build_y_exact holds its verdict per (r, g).  One product per lane finds out
                 // whether the warp has such a pixel at all (4 warps in 10 do), one vote per column where.
-                f32x2 prod = mul2(mul2(mul2(res[0], res[1]), mul2(res[2], res[3])), mul2(mul2(res[4], res[5]), mul2(res[6], res[7])));
+                const f32x2 prod = mul2(mul2(mul2(res[0], res[1]), mul2(res[2], res[3])), mul2(mul2(res[4], res[5]), mul2(res[6], res[7])));
                 if (__any_sync(0xffffffffu, lo2(prod) * hi2(prod) == 0.0f)) {
 #pragma unroll
                     for (int x = 0; x < 8; ++x) {
                         const bool za = lo2(res[x]) == 0.0f, zb = hi2(res[x]) == 0.0f;
                         if (__any_sync(0xffffffffu, za || zb)) {
                             float ca = 0.0f, cb = 0.0f;       // (the pixel's r and g come from the staged rows again: the words are dead by now)
-                            if (za) ca = float(int(__ldg(p.y_exact + (uint32_t(pa[x]) | (uint32_t(pa[16 * C::kRow + x]) << 8)))));
-                            if (zb) cb = float(int(__ldg(p.y_exact + (uint32_t(pb[x]) | (uint32_t(pb[16 * C::kRow + x]) << 8)))));
+                            if (za) ca = float(int(__ldg(p.y_exact + (lds8(pa + x) | (lds8(pa + 16 * C::kRow + x) << 8)))));
+                            if (zb) cb = float(int(__ldg(p.y_exact + (lds8(pb + x) | (lds8(pb + 16 * C::kRow + x) << 8)))));
                             y2[x] = add2(y2[x], pk2(ca, cb));
                         }
                     }
@@ -338,9 +453,8 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 4 : 2) k_fwd_transform2(const
             } else {
                 // chroma: the exact cases (r == g and b - r even, ...) are a few per cent of natural samples, so the formulas are
                 // evaluated the way the reference does, in FP64 (half rate on this part) -- 8 samples per lane, a quarter of the pixels
-                const int row = min(2 * int(sub), hlast);
-                const uint8_t* pa = s_in + row * C::kRow + mcu * 16u;
-                const uint4 rv = *reinterpret_cast<const uint4*>(pa), gv = *reinterpret_cast<const uint4*>(pa + 16 * C::kRow), bv = *reinterpret_cast<const uint4*>(pa + 32 * C::kRow);
+                const uint32_t pa = a_in + min(2 * int(sub), hlast) * C::kRow + mcu * 16u;
+                const uint4 rv = lds128(pa), gv = lds128(pa + 16 * C::kRow), bv = lds128(pa + 32 * C::kRow);
                 const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
                 for (int x = 0; x < 8; ++x) {          // decimation, not averaging (:116-143): the even pixels of the even rows
@@ -352,137 +466,137 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 4 : 2) k_fwd_transform2(const
                 }
             }
             aan_fdct8_x2(y2[0], y2[1], y2[2], y2[3], y2[4], y2[5], y2[6], y2[7]);
-            ulonglong2* dst = reinterpret_cast<ulonglong2*>(mid + sub * C::kPairRow);
+            const uint32_t dst = a_mid + sub * C::kPairRow;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) dst[k] = make_ulonglong2(y2[2 * k], y2[2 * k + 1]);
+            for (int k = 0; k < 4; ++k) sts128x(dst + 16 * k, y2[2 * k], y2[2 * k + 1]);
         }
         __syncwarp();
 
         // ---- phase 2: transform along y, quantisation; lane sub holds column sub of both blocks ----
+        int dcA = 0, dcB = 0;
+        uint32_t gm = 0;        // non-zero zig-zag groups: bits 0..7 block A, 8..15 block B
         if (work) {
             const uint32_t j = sub;
-            const int cls = luma ? 0 : 1;
-            f32x2 d[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) d[i] = *reinterpret_cast<const f32x2*>(mid + i * C::kPairRow + j * 8);
             f32x2 w[8];
             {
-                const ulonglong2* kq = reinterpret_cast<const ulonglong2*>(&s_tab->K[cls][j]);
-                const ulonglong2 k0 = kq[0], k1 = kq[1], k2 = kq[2], k3 = kq[3];
+                f32x2 d[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) d[k] = lds64x(a_mid + k * C::kPairRow + j * 8u);
                 aan_fdct8_x2(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
-                w[0] = mul2(d[0], k0.x), w[1] = mul2(d[1], k0.y), w[2] = mul2(d[2], k1.x), w[3] = mul2(d[3], k1.y);
-                w[4] = mul2(d[4], k2.x), w[5] = mul2(d[5], k2.y), w[6] = mul2(d[6], k3.x), w[7] = mul2(d[7], k3.y);
-            }
-            int dcA = 0, dcB = 0;
-            if (j == 0) {
-                dcA = __float2int_rz(lo2(w[0])), dcB = __float2int_rz(hi2(w[0]));
-                s_out[blkA * 64u] = int16_t(dcA), s_out[blkB * 64u] = int16_t(dcB);
-            }
-            // rows of coefficients in which some lane of the warp may quantise to a non-zero value: |w| >= 1 - 2 Gmax.  The
-            // larger magnitude of the pair per row, the warp's maximum of its bit pattern (REDUX), one uniform compare.
-            const uint32_t thr = s_tab->thr[cls];
-            uint32_t gm = 0;        // non-zero zig-zag groups: bits 0..7 block A, 8..15 block B
-            const uint2 izz = s_tab->izz[j];
-            const float* G = s_tab->G[cls][j];
+                const uint32_t kq = a_tab + uint32_t(offsetof(Q2Tab, K)) + (cls * 8u + j) * 64u;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float a = fmaxf(fabsf(lo2(w[i])), fabsf(hi2(w[i])));
-                if (i == 0) a = j ? a : 0.0f;                                   // the DC coefficient went its own way
-                if (__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(a) : 0u) < thr) continue;
-                const uint32_t zz = __byte_perm(i < 4 ? izz.x : izz.y, 0, 0x4440 + (i & 3));
-                const float g = G[i];
-                const f32x2 mg = pk2(kMagic15, kMagic15);
-                const f32x2 dl = sub2(w[i], sub2(add2(w[i], mg), mg));          // w - rint(w)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const float wv = h ? hi2(w[i]) : lo2(w[i]);
-                    const float dv = h ? hi2(dl) : lo2(dl);
-                    const uint32_t blk = h ? blkB : blkA;
-                    const int q = __float2int_rz(wv);
-                    if ((i | j) != 0 && valid) {
-                        if (fabsf(dv) < g && fabsf(wv) > 0.5f) push_fix(nfix_p, s_fix, (blk << 6) | uint32_t(i * 8) | j);
-                        if (q != 0) {
-                            s_out[blk * 64u + zz] = int16_t(q);
-                            gm |= 1u << ((zz >> 3) + 8u * h);
-                        }
-                    }
+                for (int k = 0; k < 8; k += 2) {
+                    const uint4 kk = lds128(kq + 8 * k);
+                    w[k] = mul2(d[k], (unsigned long long)kk.x | ((unsigned long long)kk.y << 32));
+                    w[k + 1] = mul2(d[k + 1], (unsigned long long)kk.z | ((unsigned long long)kk.w << 32));
                 }
             }
-            if (__any_sync(0xffffffffu, gm != 0u)) {
+            if (j == 0) {
+                dcA = __float2int_rz(lo2(w[0])), dcB = __float2int_rz(hi2(w[0]));
+                sts16(a_outA, dcA), sts16(a_outA + dAB, dcB);
+            }
+            // rows of coefficients in which some lane of the warp may quantise to a non-zero value: |w| >= 1 - 2 Gmax.  The
+            // larger magnitude of the pair per row, the warp's maximum of its bit pattern (REDUX), one uniform compare; the
+            // five high rows (rarely alive in photographic content) share a first test.
+            const uint32_t thr = lds32(a_tab + uint32_t(offsetof(Q2Tab, thr)) + 4u * cls);
+            const uint2 izz = lds64(a_tab + uint32_t(offsetof(Q2Tab, izz)) + 8u * j);
+            const uint32_t a_g = a_tab + uint32_t(offsetof(Q2Tab, G)) + (cls * 8u + j) * 32u;
+            float am[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) am[k] = fmaxf(fabsf(lo2(w[k])), fabsf(hi2(w[k])));
+            if (j == 0) am[0] = 0.0f;                                   // the DC coefficient went its own way
+            const float hi_rows = fmaxf(fmaxf(fmaxf(am[3], am[4]), fmaxf(am[5], am[6])), am[7]);
+            const bool any_hi = __reduce_max_sync(0xffffffffu, valid ? __float_as_uint(hi_rows) : 0u) >= thr;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k >= 3 && !any_hi) break;
+                if (__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(am[k]) : 0u) < thr) continue;
+                const uint32_t zz = __byte_perm(k < 4 ? izz.x : izz.y, 0, 0x4440 + (k & 3));
+                const float g = __uint_as_float(lds32(a_g + 4u * k));
+                const f32x2 mg = pk2(kMagic15, kMagic15);
+                const f32x2 dl = sub2(w[k], sub2(add2(w[k], mg), mg));          // w - rint(w)
+                const uint32_t a_o = a_outA + 2u * zz, gbit = 1u << (zz >> 3);
+                if ((k | j) != 0 && valid) {
+                    const float wa = lo2(w[k]), wb = hi2(w[k]);
+                    const int qa = __float2int_rz(wa), qb = __float2int_rz(wb);
+                    if (fabsf(lo2(dl)) < g && fabsf(wa) > 0.5f) push_fix_w(a_cnt, a_fix, ((blkA) << 6) | uint32_t(k * 8) | j);
+                    if (fabsf(hi2(dl)) < g && fabsf(wb) > 0.5f) push_fix_w(a_cnt, a_fix, ((blkA + (dAB >> 7)) << 6) | uint32_t(k * 8) | j);
+                    if (qa != 0) sts16(a_o, qa), gm |= gbit;
+                    if (qb != 0) sts16(a_o + dAB, qb), gm |= gbit << 8;
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 2b: this warp's guard-band queue, FP64, eight lanes per entry ----
+        {
+            const uint32_t nfix = lds32(a_cnt);
+            if (nfix) {
+                const uint32_t s8 = uint32_t(lane) & 7u;
+                const bool overflow = nfix > uint32_t(kWarpFix);
+                // overflow (adversarial content): every AC coefficient of the warp's eight blocks
+                const uint32_t nent = overflow ? 8u * 63u : nfix;
+                const uint32_t wblk0 = luma ? uint32_t(warp) * 12u : (uint32_t(warp) - 2u * T / 4u) * 24u + 4u;      // first block of the warp's pairs
+                for (uint32_t e0 = 0; e0 < nent; e0 += 4) {
+                    const uint32_t e = e0 + (uint32_t(lane) >> 3);
+                    bool actv = e < nent;
+                    uint32_t ent;
+                    if (overflow) {
+                        const uint32_t b8 = e / 63u, ij = e - b8 * 63u + 1u;     // the warp's b8-th block: luma m*6 + {0,1,2,3} of two MCUs, chroma m*6 + {4,5} of four
+                        const uint32_t blk = luma ? wblk0 + (b8 >> 2) * 6u + (b8 & 3u) : wblk0 + (b8 >> 1) * 6u + (b8 & 1u);
+                        ent = (blk << 6) | ij;
+                    } else {
+                        ent = actv ? lds32(a_fix + 2u * (e & ~1u)) >> (16u * (e & 1u)) & 0xffffu : 0u;
+                    }
+                    const uint32_t blk = (ent >> 6) & 0x7fu, ij = ent & 63u, ci = ij >> 3, cj = ij & 7u;
+                    actv = actv && blk / 6u < nvalid;
+                    const double* cjp = &gCosRef[cj * 8];
+                    double row = 0.0;
+#pragma unroll 1
+                    for (int x = 0; x < 8; ++x) row = fma(double(tile_sample_s<C::kRow>(a_in, actv ? blk : blkA, int(s8), x, hlast, p.gray)), cjp[x], row);
+                    double part = row * gCosRef[ci * 8 + s8];
+                    part += __shfl_xor_sync(0xffffffffu, part, 1);
+                    part += __shfl_xor_sync(0xffffffffu, part, 2);
+                    part += __shfl_xor_sync(0xffffffffu, part, 4);
+                    if (actv && s8 == 0) {
+                        const int q = cC.quant[(blk % 6u) >= 4u][ij];
+                        const int v = requant_finish_s<C::kRow>(part, a_in, blk, int(ci), int(cj), q, hlast, p.gray, p.guard_counter);
+                        const uint32_t zz = cC.izz[ij];
+                        sts16(sm + C::oOut + ob * C::kOut + blk * 128u + 2u * zz, v);
+                    }
+                }
+                __syncwarp();
+                // a fixed-up coefficient may have become non-zero: the side information is recomputed from the staging buffer
+                {
+                    const uint32_t a_o = a_outA + sub * 16u;
+                    const uint4 ga = lds128(a_o), gb = lds128(a_o + dAB);
+                    const bool nza = ((sub ? ga.x : (ga.x >> 16)) | ga.y | ga.z | ga.w) != 0u, nzb = ((sub ? gb.x : (gb.x >> 16)) | gb.y | gb.z | gb.w) != 0u;
+                    const uint32_t ba = __ballot_sync(0xffffffffu, nza), bb = __ballot_sync(0xffffffffu, nzb);
+                    gm = ((ba >> (lane & 24)) & 0xffu) | (((bb >> (lane & 24)) & 0xffu) << 8);
+                }
+                if (lane == 0) sts32(a_cnt, 0u);
+            } else if (__any_sync(0xffffffffu, gm != 0u)) {
                 gm |= __shfl_xor_sync(0xffffffffu, gm, 1);
                 gm |= __shfl_xor_sync(0xffffffffu, gm, 2);
                 gm |= __shfl_xor_sync(0xffffffffu, gm, 4);
             }
-            if (j == 0) {
-                s_meta[blkA] = (uint32_t(dcA) & 0xffffu) | ((gm & 0xffu) << 16);
-                s_meta[blkB] = (uint32_t(dcB) & 0xffffu) | ((gm & 0xff00u) << 8);
-            }
-        } else if (sub == 0) {
-            s_meta[blkA] = 0, s_meta[blkB] = 0;
         }
-        fence_async_smem();      // the staging buffer is read by the async proxy (bulk store)
-        if (t == 0) bulk_wait_read0();      // the previous tile's store has read the other staging buffer: the next tile may fill it
-        __syncthreads();
-        if (t == 0) s_nfix[(it + 2u) % 3u] = 0;      // the previous tile's queue length: read by everyone before this barrier, used again by tile it + 2
-
-        // ---- phase 2b: dense FP64 re-evaluation of the guard-band queue ----
-        {
-            const uint32_t nfix = *nfix_p;
-            if (nfix) {
-                if (nfix > kFixCap) {
-                    // queue overflow (adversarial content): every AC coefficient of the tile is re-evaluated
-                    for (uint32_t e = t; e < nvalid * 6u * 64u; e += C::kThreads) {
-                        const uint32_t blk = e >> 6, ij = e & 63u, i = ij >> 3, j = ij & 7u;
-                        if (ij == 0 || (p.gray && blk % 6u >= 4u)) continue;
-                        double acc = 0.0;
-                        for (int y = 0; y < 8; ++y) {
-                            double row = 0.0;
-                            for (int x = 0; x < 8; ++x) row = fma(double(tile_sample<C::kRow>(s_in, blk, y, x, hlast, p.gray)), cC.cos_ref[j * 8 + x], row);
-                            acc = fma(row, cC.cos_ref[i * 8 + y], acc);
-                        }
-                        const int q = cC.quant[(blk % 6u) >= 4u][ij];
-                        const int v = requant_finish2<C::kRow>(acc, s_in, blk, int(i), int(j), q, hlast, p.gray, p.guard_counter);
-                        s_out[blk * 64u + cC.izz[ij]] = int16_t(v);
-                        if (v) atomicOr(&s_meta[blk], 1u << (16 + (cC.izz[ij] >> 3)));
-                    }
-                } else {
-                    // eight lanes per entry: lane s evaluates row s of the separable sum, a 3-step butterfly adds the rows
-                    const uint32_t s = uint32_t(t) & 7u;
-                    for (uint32_t e0 = 0; e0 < nfix; e0 += C::kThreads / 8) {
-                        const uint32_t e = e0 + (uint32_t(t) >> 3);
-                        const bool actv = e < nfix;
-                        const uint32_t ent = actv ? uint32_t(s_fix[e]) : 0u;
-                        const uint32_t blk = ent >> 6, ij = ent & 63u, i = ij >> 3, j = ij & 7u;
-                        const double* cj = &gCosRef[j * 8];
-                        double row = 0.0;
-#pragma unroll 1
-                        for (int x = 0; x < 8; ++x) row = fma(double(tile_sample<C::kRow>(s_in, blk, int(s), x, hlast, p.gray)), cj[x], row);
-                        double part = row * gCosRef[i * 8 + s];
-                        part += __shfl_xor_sync(0xffffffffu, part, 1);
-                        part += __shfl_xor_sync(0xffffffffu, part, 2);
-                        part += __shfl_xor_sync(0xffffffffu, part, 4);
-                        if (actv && s == 0) {
-                            const int q = cC.quant[(blk % 6u) >= 4u][ij];
-                            const int v = requant_finish2<C::kRow>(part, s_in, blk, int(i), int(j), q, hlast, p.gray, p.guard_counter);
-                            s_out[blk * 64u + cC.izz[ij]] = int16_t(v);
-                            if (v) atomicOr(&s_meta[blk], 1u << (16 + (cC.izz[ij] >> 3)));
-                        }
-                    }
-                }
-                fence_async_smem();
-                __syncthreads();
-            }
+        // side information of the entropy coder: DC coefficient + non-zero groups of both blocks, straight from the registers
+        if (p.bmeta && sub == 0 && valid) {
+            uint32_t* meta = p.bmeta + size_t(img) * (p.coef_stride >> 6) + (size_t(my) * p.HU + mx0) * 6 + blkA;
+            meta[0] = (uint32_t(dcA) & 0xffffu) | ((gm & 0xffu) << 16);
+            meta[dAB >> 7] = (uint32_t(dcB) & 0xffffu) | ((gm & 0xff00u) << 8);
         }
-
-        // ---- phase 3: one bulk store of the tile's coefficients (scan order), side information by plain stores ----
-        const size_t mcu0 = size_t(my) * p.HU + mx0;
-        if (t == 0) {
-            bulk_s2g(p.coefs + size_t(img) * p.coef_stride + mcu0 * 384, smem_u32(s_out), nvalid * 768u);
-            bulk_commit();
+        // done with the stage and with the staging buffer: tell the DMA warp
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(bar_out_full + 8u * ob);
+            mbar_arrive(bar_in_empty + 8u * st);
         }
-        if (p.bmeta && uint32_t(t) < nvalid * 6u) p.bmeta[size_t(img) * (p.coef_stride >> 6) + mcu0 * 6 + t] = s_meta[t];
+        if (++st == NST) st = 0, stpar ^= 1u;
+        advance(img, my, bx);
     }
-    if (t == 0) bulk_wait_read0();
 }
 
 }  // namespace jz
