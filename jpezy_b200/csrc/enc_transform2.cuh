@@ -207,6 +207,7 @@ __device__ __forceinline__ uint32_t lds8(uint32_t a)
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void sts64x(uint32_t a, f32x2 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
 __device__ __forceinline__ void sts128x(uint32_t a, f32x2 lo, f32x2 hi) { asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a), "l"(lo), "l"(hi) : "memory"); }
 __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
 {
@@ -216,12 +217,15 @@ __device__ __forceinline__ void sts16(uint32_t a, int v) { asm volatile("st.shar
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 // wait with a watchdog: a protocol error must trap, not hang the device
+// (try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes instead of polling -- the polling
+// loop of the first version was a third of all executed instructions)
 __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity)
 {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
-    }
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+        if (!ok && ++spins > (1u << 16)) __trap();
+    } while (!ok);
 }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
@@ -301,7 +305,8 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
 {
     using C = Fwd2<T, NST>;
     extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t sm = smem_u32(smem);
+    uint32_t sm = smem_u32(smem);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sm));       // (kept in a register: rematerialising the shared window base costs three uniform ops per use)
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t bar_in_full = sm + C::oBar, bar_in_empty = bar_in_full + 8u * NST, bar_out_full = bar_in_empty + 8u * NST, bar_out_empty = bar_out_full + 16u;
 
@@ -370,10 +375,8 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
             const uint32_t mx0 = bx * T, nvalid = min(uint32_t(T), p.HU - mx0);
             bulk_s2g(p.coefs + size_t(img) * p.coef_stride + (size_t(my) * p.HU + mx0) * 384, sm + C::oOut + ob * C::kOut, nvalid * 768u);
             bulk_commit();
-            if (i >= 1) {
-                bulk_wait_read1();                       // the previous tile's store has read its staging buffer
-                mbar_arrive(bar_out_empty + 8u * (ob ^ 1u));
-            }
+            bulk_wait_read0();                           // the store has read the staging buffer (not: has reached memory)
+            mbar_arrive(bar_out_empty + 8u * ob);
             advance(img, my, bx);
         }
         bulk_wait_read0();
@@ -468,7 +471,7 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
             aan_fdct8_x2(y2[0], y2[1], y2[2], y2[3], y2[4], y2[5], y2[6], y2[7]);
             const uint32_t dst = a_mid + sub * C::kPairRow;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) sts128x(dst + 16 * k, y2[2 * k], y2[2 * k + 1]);
+            for (int k = 0; k < 8; ++k) sts64x(dst + 8 * k, y2[k]);       // (16-byte stores would need the pairs in adjacent registers)
         }
         __syncwarp();
 
