@@ -175,10 +175,21 @@ JPEZYB200_API int jpezyb200_decode(jpezyb200_ctx* ctx, const uint8_t* scan, size
 
 /* Batch, device resident, all images share the frame descriptor.  Image i: segment at
  * d_scan + i*slot_bytes with length h_scan_bytes[i] (HOST array: the file length is host knowledge),
- * planes at d_r + i*plane_bytes.  d_status[i] (device, may be NULL) receives 0 or JPEZYB200_ECORRUPT. */
+ * planes at d_r + i*plane_bytes.  d_status[i] (device, may be NULL) receives 0, JPEZYB200_ECORRUPT or JPEZYB200_EAGAIN (the
+ * self-synchronising decoder did not reach its fixed point in the enqueued launches: decode that image again with
+ * JPEZYB200_OPT_SYNC_ROUNDS = 0, the host-polled loop). */
 JPEZYB200_API int jpezyb200_decode_batch_dev(jpezyb200_ctx* ctx, const uint8_t* d_scan, size_t slot_bytes, const uint64_t* h_scan_bytes,
                                uint32_t nimg, const jpezyb200_frame* f, int gray, uint8_t* d_r, uint8_t* d_g, uint8_t* d_b,
                                size_t plane_bytes, int32_t* d_status, void* stream);
+
+/* The same with the segment lengths in DEVICE memory (d_scan_bytes, e.g. the d_scan_bytes output of jpezyb200_encode_batch_dev):
+ * a device-resident transcode needs no host round trip between the encoder and the decoder.  The launch is sized for segments
+ * of at most max_scan_bytes (1..slot_bytes); an image whose length turns out larger is not decoded and reports
+ * JPEZYB200_ECAPACITY in d_status.  The file-length semantics of the reference (src/decoder/jpezy_decoder.hpp:41-72, the
+ * decoder owns a file of known size) stay available through the host-array form above. */
+JPEZYB200_API int jpezyb200_decode_batch_dev2(jpezyb200_ctx* ctx, const uint8_t* d_scan, size_t slot_bytes, const uint64_t* d_scan_bytes,
+                                uint64_t max_scan_bytes, uint32_t nimg, const jpezyb200_frame* f, int gray, uint8_t* d_r, uint8_t* d_g,
+                                uint8_t* d_b, size_t plane_bytes, int32_t* d_status, void* stream);
 
 /* Batch in HOST memory, pipelined like jpezyb200_encode_batch: segment i at scan + i*slot_bytes (scan_bytes[i] bytes), planes of
  * image i at r + i*plane_bytes.  status (host, may be NULL) receives 0 or JPEZYB200_ECORRUPT per image. */

@@ -14,7 +14,7 @@ EXPORTS = [
     "jpezyb200_abi_version", "jpezyb200_ctx_create", "jpezyb200_ctx_destroy", "jpezyb200_strerror", "jpezyb200_last_error",
     "jpezyb200_set_option", "jpezyb200_get_stat", "jpezyb200_encode", "jpezyb200_encode_batch_dev",
     "jpezyb200_transform_fwd_dev", "jpezyb200_entropy_encode_dev", "jpezyb200_plane_bytes", "jpezyb200_default_frame",
-    "jpezyb200_decode", "jpezyb200_decode_batch_dev", "jpezyb200_entropy_decode_dev", "jpezyb200_transform_inv_dev",
+    "jpezyb200_decode", "jpezyb200_decode_batch_dev", "jpezyb200_decode_batch_dev2", "jpezyb200_entropy_decode_dev", "jpezyb200_transform_inv_dev",
     "jpezyb200_synth_dev", "jpezyb200_synth_rows_dev", "jpezyb200_shard_encode_a", "jpezyb200_shard_encode_b",
     "jpezyb200_shard_encode_c", "jpezyb200_shard_encode_d", "jpezyb200_ipc_alloc", "jpezyb200_ipc_open", "jpezyb200_ipc_close",
     "jpezyb200_ipc_free", "jpezyb200_shard_decode_dev", "jpezyb200_encode_batch", "jpezyb200_decode_batch", "jpezyb200_read_sizes",
@@ -81,6 +81,7 @@ def load_library():
     L.jpezyb200_default_frame.argtypes = [u32, u32, C.POINTER(Frame)]
     L.jpezyb200_decode.argtypes = [vp, u8p, sz, C.POINTER(Frame), C.c_int, u8p, u8p, u8p, sz]
     L.jpezyb200_decode_batch_dev.argtypes = [vp, u8p, sz, u64p, u32, C.POINTER(Frame), C.c_int, u8p, u8p, u8p, sz, vp, vp]
+    L.jpezyb200_decode_batch_dev2.argtypes = [vp, u8p, sz, vp, C.c_uint64, u32, C.POINTER(Frame), C.c_int, u8p, u8p, u8p, sz, vp, vp]
     L.jpezyb200_entropy_decode_dev.argtypes = [vp, u8p, sz, u64p, u32, C.POINTER(Frame), i16p, vp, vp]
     L.jpezyb200_transform_inv_dev.argtypes = [vp, i16p, C.POINTER(Frame), u32, C.c_int, u8p, u8p, u8p, sz, vp]
     L.jpezyb200_synth_dev.argtypes = [vp, u8p, u8p, u8p, u32, u32, u32, u32, C.c_int, vp]
@@ -210,6 +211,13 @@ class Context:
         hs = np.ascontiguousarray(h_scan_bytes, dtype=np.uint64)
         self._chk(self.lib.jpezyb200_decode_batch_dev(self.h, _dp(d_scan), slot_bytes, _dp(hs), nimg, C.byref(frame), int(gray),
                                                       _dp(d_r), _dp(d_g), _dp(d_b), plane_len, _dp(d_status), stream))
+
+    def decode_batch_dev2(self, d_scan, slot_bytes, d_scan_bytes, max_scan_bytes, nimg, frame, gray, d_r, d_g, d_b, plane_len,
+                          d_status=None, stream=None):
+        """segment lengths read from device memory (no host round trip behind the encoder)"""
+        self._chk(self.lib.jpezyb200_decode_batch_dev2(self.h, _dp(d_scan), slot_bytes, _dp(d_scan_bytes), int(max_scan_bytes), nimg,
+                                                       C.byref(frame), int(gray), _dp(d_r), _dp(d_g), _dp(d_b), plane_len,
+                                                       _dp(d_status), stream))
 
     def entropy_decode_dev(self, d_scan, slot_bytes, h_scan_bytes, nimg, frame, d_coefs, d_status=None, stream=None):
         import numpy as np

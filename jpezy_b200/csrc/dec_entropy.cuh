@@ -78,6 +78,9 @@ struct DecParams {
     const uint64_t* scan_bytes;   // device copy of the host array [nimg]
     uint64_t inline_bytes[8];     // ninline != 0 (small batches): the sizes travel as kernel arguments and k_unstuff_count
     uint32_t ninline;             // fills scan_bytes itself -- no host-to-device copy in front of the first kernel
+    const uint64_t* ext_bytes;    // != nullptr: the lengths are read from this device array (jpezyb200_decode_batch_dev2); k_unstuff_count
+                                  // copies them into scan_bytes, refusing (length 0, JPEZYB200_ECAPACITY) what exceeds max_bytes
+    uint64_t max_bytes;           // capacity the launch was sized for
     // un-stuffed stream
     uint8_t* ustream;         // [nimg][uslot]  (uslot multiple of 16, 32 bytes of zero slack)
     size_t uslot;
@@ -370,8 +373,9 @@ __global__ void __launch_bounds__(kDecThreads) k_unstuff_count(const DecParams p
         if (threadIdx.x < kMaxSyncRounds) p.changed[threadIdx.x] = 0;
         if (threadIdx.x < 2) p.iters_stat[threadIdx.x] = 0;
     }
-    if (p.ninline && blockIdx.x == 0 && threadIdx.x == 0) const_cast<uint64_t*>(p.scan_bytes)[img] = p.inline_bytes[img & 7];
-    const uint64_t n = p.ninline ? p.inline_bytes[img & 7] : p.scan_bytes[img];
+    uint64_t n = p.ext_bytes ? p.ext_bytes[img] : (p.ninline ? p.inline_bytes[img & 7] : p.scan_bytes[img]);
+    if (p.ext_bytes && n > p.max_bytes) n = 0;       // does not fit what the launch was sized for: nothing is decoded (k_scan_blocks reports it)
+    if ((p.ninline || p.ext_bytes) && blockIdx.x == 0 && threadIdx.x == 0) const_cast<uint64_t*>(p.scan_bytes)[img] = n;
     const uint8_t* src = p.scan + img * p.slot;
     const uint32_t nch = uint32_t((n + 4095) / 4096);
     for (uint32_t ch = blockIdx.x; ch < nch; ch += gridDim.x) {
@@ -611,7 +615,10 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const DecParams p, const u
     if (threadIdx.x == 0) {
         // not a fixed point after the enqueued launches: the caller has to run the host-driven loop (JPEZYB200_EAGAIN)
         const bool converged = p.rounds == 0 || p.changed[p.rounds] == 0;
-        if (p.status) p.status[img] = !converged ? JPEZYB200_EAGAIN : (s_carry >= p.nblk ? 0 : JPEZYB200_ECORRUPT);
+        if (p.status) {
+            p.status[img] = !converged ? JPEZYB200_EAGAIN : (s_carry >= p.nblk ? 0 : JPEZYB200_ECORRUPT);
+            if (p.ext_bytes && p.ext_bytes[img] > p.max_bytes) p.status[img] = JPEZYB200_ECAPACITY;
+        }
         if (img == 0) {
             unsigned long long n = 1 + p.rounds_host;
             for (uint32_t k = 1; k <= p.rounds; ++k) n += (k == 1 || p.changed[k - 1] != 0) ? 1ull : 0ull;

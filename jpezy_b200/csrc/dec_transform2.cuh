@@ -31,18 +31,20 @@ namespace jz {
 
 // per frame descriptor (quantisation tables), laid out for the column lanes; built by k_build_inv2_tab when the tables change
 struct Inv2Tab {
-    float2 M[3][8][8];     // [component][u][v]: (M, M), M = q * aan_v * aan_u / 8 of coefficient (v, u)
-    float Wg[3][8][8];     // [component][u][v]: guard-band weight per unit |coefficient|
+    float2 M[2][8][8];     // [pair class][u][v]: (M of block A, M of block B), M = q * aan_v * aan_u / 8 of coefficient (v, u);
+                           // class 0 = two luma blocks, class 1 = Cb | Cr (their quantisation tables may differ)
+    float2 Wg[2][8][8];    // [pair class][u][v]: guard-band weights per unit |coefficient|
     uint2 zoff[8];         // [u]: byte offsets (2 * zig-zag position) of coefficients (0..7, u), one byte each
 };
 
 __global__ void k_build_inv2_tab(const InvParams p, Inv2Tab* __restrict__ tab)
 {
     pdl_wait();
-    const int t = threadIdx.x;      // 192 threads: component, natural position
+    const int t = threadIdx.x;      // 128 threads: pair class, natural position
     const int c = t >> 6, nat = t & 63, v = nat >> 3, u = nat & 7;
-    tab->M[c][u][v] = make_float2(p.M[c][nat], p.M[c][nat]);
-    tab->Wg[c][u][v] = p.Wg[c][nat];
+    const int ca = c ? 1 : 0, cb = c ? 2 : 0;
+    tab->M[c][u][v] = make_float2(p.M[ca][nat], p.M[cb][nat]);
+    tab->Wg[c][u][v] = make_float2(p.Wg[ca][nat], p.Wg[cb][nat]);
     if (t < 8) {
         uint32_t w[2] = {0, 0};
         for (int vv = 0; vv < 8; ++vv) w[vv >> 2] |= uint32_t(cC.izz[vv * 8 + t] * 2) << (8 * (vv & 3));
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 5 : 2) k_inv_transform2(const
         dcA = __ldg(dc + blkA), dcB = __ldg(dc + blkB);
     }
 
-    mbar_wait(bar, 0);
+    mbar_wait_wd(bar, 0);
 
     if (luma || !p.gray) {
         // ---- masks of the non-zero zig-zag groups: lane sub looks at group sub of both blocks ----
@@ -280,8 +282,9 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 5 : 2) k_inv_transform2(const
             f32x2 gs = pk2(0.0f, 0.0f);
             {
                 const uint2 zo = __ldg(&tab->zoff[u]);
-                const ulonglong2* mq = reinterpret_cast<const ulonglong2*>(&tab->M[compA][u][0]);
-                const float4* wq = reinterpret_cast<const float4*>(&tab->Wg[compA][u][0]);
+                const int cls = luma ? 0 : 1;
+                const ulonglong2* mq = reinterpret_cast<const ulonglong2*>(&tab->M[cls][u][0]);
+                const ulonglong2* wq = reinterpret_cast<const ulonglong2*>(&tab->Wg[cls][u][0]);
                 const uint32_t base = smem_u32(cA);
 #define JZ_LOAD_COEF(V, ZW, K, MM, WW)                                                                                   \
     {                                                                                                                     \
@@ -291,30 +294,28 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 5 : 2) k_inv_transform2(const
         asm volatile("ld.shared.s16 %0, [%1];" : "=h"(cb) : "r"(ad + dAB));                                               \
         const f32x2 f = pk2(float(int(ca)), float(int(cb)));                                                              \
         d[V] = mul2(f, MM);                                                                                               \
-        const f32x2 g = mul2(f, pk2(WW, WW));                                                                             \
+        const f32x2 g = mul2(f, WW);                                                                                      \
         gs = add2(gs, pk2(fabsf(lo2(g)), fabsf(hi2(g))));                                                                 \
     }
-                const ulonglong2 m01 = __ldg(mq), m23 = __ldg(mq + 1);
-                const float4 w03 = __ldg(wq);
-                JZ_LOAD_COEF(0, zo.x, 0, m01.x, w03.x)
+                const ulonglong2 m01 = __ldg(mq), m23 = __ldg(mq + 1), w01 = __ldg(wq), w23 = __ldg(wq + 1);
+                JZ_LOAD_COEF(0, zo.x, 0, m01.x, w01.x)
                 if (u == 0) {      // the DC coefficient is in registers (dense array or position 0 of the block)
                     const f32x2 f = pk2(float(dcA), float(dcB));
                     d[0] = mul2(f, m01.x);
-                    const f32x2 g = mul2(f, pk2(w03.x, w03.x));
+                    const f32x2 g = mul2(f, w01.x);
                     gs = pk2(fabsf(lo2(g)), fabsf(hi2(g)));
                 }
-                JZ_LOAD_COEF(1, zo.x, 1, m01.y, w03.y)
-                JZ_LOAD_COEF(2, zo.x, 2, m23.x, w03.z)
+                JZ_LOAD_COEF(1, zo.x, 1, m01.y, w01.y)
+                JZ_LOAD_COEF(2, zo.x, 2, m23.x, w23.x)
                 if (pruned) {
                     d[3] = d[4] = d[5] = d[6] = d[7] = pk2(0.0f, 0.0f);
                 } else {
-                    const ulonglong2 m45 = __ldg(mq + 2), m67 = __ldg(mq + 3);
-                    const float4 w47 = __ldg(wq + 1);
-                    JZ_LOAD_COEF(3, zo.x, 3, m23.y, w03.w)
-                    JZ_LOAD_COEF(4, zo.y, 0, m45.x, w47.x)
-                    JZ_LOAD_COEF(5, zo.y, 1, m45.y, w47.y)
-                    JZ_LOAD_COEF(6, zo.y, 2, m67.x, w47.z)
-                    JZ_LOAD_COEF(7, zo.y, 3, m67.y, w47.w)
+                    const ulonglong2 m45 = __ldg(mq + 2), m67 = __ldg(mq + 3), w45 = __ldg(wq + 2), w67 = __ldg(wq + 3);
+                    JZ_LOAD_COEF(3, zo.x, 3, m23.y, w23.y)
+                    JZ_LOAD_COEF(4, zo.y, 0, m45.x, w45.x)
+                    JZ_LOAD_COEF(5, zo.y, 1, m45.y, w45.y)
+                    JZ_LOAD_COEF(6, zo.y, 2, m67.x, w67.x)
+                    JZ_LOAD_COEF(7, zo.y, 3, m67.y, w67.y)
                 }
 #undef JZ_LOAD_COEF
             }

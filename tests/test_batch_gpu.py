@@ -98,3 +98,45 @@ def test_device_chain_with_read_sizes(ctx, oracle):
             assert (out[0, k] == r0).all() and (out[1, k] == g0).all() and (out[2, k] == b0).all()
     finally:
         torch.cuda.set_stream(torch.cuda.default_stream())
+
+
+@pytest.mark.parametrize("nimg", [1, 11])
+def test_device_resident_lengths_equal_host_lengths(ctx, nimg):
+    """jpezyb200_decode_batch_dev2 (segment lengths read from device memory: the encoder's own d_scan_bytes output) must give
+    exactly what jpezyb200_decode_batch_dev gives with the lengths in a host array; a segment longer than the launch was
+    sized for is refused with JPEZYB200_ECAPACITY, the others of the batch still decode"""
+    W, H = 208, 112
+    frame = J.default_frame(W, H)
+    pl = capi.plane_bytes(frame)
+    slot = W * H * 3
+    d_in = torch.empty((3, nimg, H, W), dtype=torch.uint8, device="cuda")
+    for k in range(nimg):
+        im = J.synth.image(k % 2, W, H, frame=k)        # photo / noise alternate: very different segment lengths
+        for c in range(3):
+            d_in[c, k].copy_(torch.from_numpy(im[c]))
+    d_scan = torch.zeros((nimg, slot), dtype=torch.uint8, device="cuda")
+    d_nb = torch.zeros(nimg, dtype=torch.int64, device="cuda")
+    ctx.encode_batch_dev(d_in[0], d_in[1], d_in[2], W, H, nimg, False, d_scan, slot, d_nb, None)
+    torch.cuda.synchronize()
+    h_nb = d_nb.cpu().numpy().astype(np.uint64)
+    out_h = torch.zeros((3, nimg, pl), dtype=torch.uint8, device="cuda")
+    out_d = torch.full((3, nimg, pl), 0x33, dtype=torch.uint8, device="cuda")
+    st_h = torch.full((nimg,), -1, dtype=torch.int32, device="cuda")
+    st_d = torch.full((nimg,), -1, dtype=torch.int32, device="cuda")
+    ctx.decode_batch_dev(d_scan, slot, h_nb, nimg, frame, False, out_h[0], out_h[1], out_h[2], pl, st_h)
+    ctx.decode_batch_dev2(d_scan, slot, d_nb, int(h_nb.max()), nimg, frame, False, out_d[0], out_d[1], out_d[2], pl, st_d)
+    torch.cuda.synchronize()
+    assert (st_h == 0).all() and (st_d == 0).all()
+    assert torch.equal(out_h, out_d)
+    if nimg > 1:
+        # sized for the shortest segment + 1 byte: only the images that fit are decoded
+        cap = int(h_nb.min()) + 1
+        st_c = torch.full((nimg,), -1, dtype=torch.int32, device="cuda")
+        ctx.decode_batch_dev2(d_scan, slot, d_nb, cap, nimg, frame, False, out_d[0], out_d[1], out_d[2], pl, st_c)
+        torch.cuda.synchronize()
+        st = st_c.cpu().numpy()
+        fits = h_nb <= cap
+        assert fits.any() and (~fits).any()
+        assert (st[fits] == 0).all() and (st[~fits] == capi.ECAPACITY).all()
+        for k in np.nonzero(fits)[0]:
+            assert torch.equal(out_h[:, k], out_d[:, k])
