@@ -66,6 +66,9 @@ enum {
                                      (validation build)                                           */
     JPEZYB200_OPT_BATCH_GROUP_BYTES = 4, /* jpezyb200_encode_batch / decode_batch: host<->device bytes per pipeline stage
                                      (default 96 MiB; images per group = value / (3 * pixels), at least 1)      */
+    JPEZYB200_OPT_SHARD_SCRATCH_BYTES = 5, /* jpezyb200_shard_encode_*: bytes of device scratch for this rank's un-stuffed bits;
+                                     0 (default) = the reference's own bound, 3 bytes per pixel of the shard.  A shard that does
+                                     not fit makes EVERY rank report overflow in phase D (no silently short segment) */
     JPEZYB200_OPT_SYNC_ROUNDS = 3 /* self-synchronisation launches enqueued after the first one by the
                                      decoder: n > 0 = exactly n, no host round trip (default 3; one is
                                      needed on ordinary streams thanks to the warm-up overlap, later ones return at once); 0 = the
@@ -192,7 +195,9 @@ JPEZYB200_API int jpezyb200_decode_batch_dev2(jpezyb200_ctx* ctx, const uint8_t*
                                 uint8_t* d_b, size_t plane_bytes, int32_t* d_status, void* stream);
 
 /* Batch in HOST memory, pipelined like jpezyb200_encode_batch: segment i at scan + i*slot_bytes (scan_bytes[i] bytes), planes of
- * image i at r + i*plane_bytes.  status (host, may be NULL) receives 0 or JPEZYB200_ECORRUPT per image. */
+ * image i at r + i*plane_bytes.  status (host, may be NULL) receives 0 or an error code per image (JPEZYB200_EAGAIN never
+ * leaves this call: such an image is decoded again with the host-polled loop).  With status == NULL the call returns the first
+ * per-image error instead of JPEZYB200_OK. */
 JPEZYB200_API int jpezyb200_decode_batch(jpezyb200_ctx* ctx, const uint8_t* scan, size_t slot_bytes, const uint64_t* scan_bytes, uint32_t nimg,
                            const jpezyb200_frame* f, int gray, uint8_t* r, uint8_t* g, uint8_t* b, size_t plane_bytes, int32_t* status);
 

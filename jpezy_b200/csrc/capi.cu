@@ -219,6 +219,10 @@ int jpezyb200_set_option(jpezyb200_ctx* ctx, int option, int64_t value)
         if (value < 1) return ctx->fail(JPEZYB200_EINVAL, "group bytes must be positive");
         ctx->group_bytes = value;
         return JPEZYB200_OK;
+    case JPEZYB200_OPT_SHARD_SCRATCH_BYTES:
+        if (value < 0) return ctx->fail(JPEZYB200_EINVAL, "scratch bytes must be >= 0");
+        ctx->shard_scratch = value;
+        return JPEZYB200_OK;
     case JPEZYB200_OPT_SYNC_ROUNDS:
         if (value < 0 || value > 64) return ctx->fail(JPEZYB200_EINVAL, "sync rounds must be in 0..64");
         ctx->sync_rounds = int(value);
@@ -262,15 +266,24 @@ struct HostPipe {
     cudaEvent_t ev[kHostBands] = {};
     uint64_t* h_sz = nullptr;      // pinned: sizes / status read back by the host
 };
+static void host_pipe_destroy(jpezyb200_ctx* ctx);
 static int host_pipe(jpezyb200_ctx* ctx, HostPipe** out)
 {
     if (!ctx->host_pipe) {
+        // built completely before it is used: a half-made pipe (a failed stream / event / pinned allocation) is torn down again
         HostPipe* hp = new (std::nothrow) HostPipe();
         if (!hp) return JPEZYB200_ENOMEM;
         ctx->host_pipe = hp;
-        JZ_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&hp->copy, cudaStreamNonBlocking));
-        for (cudaEvent_t& e : hp->ev) JZ_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        JZ_CUDA_TRY(ctx, cudaMallocHost(&hp->h_sz, 64));
+        const int rc = [&]() -> int {
+            JZ_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&hp->copy, cudaStreamNonBlocking));
+            for (cudaEvent_t& e : hp->ev) JZ_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            JZ_CUDA_TRY(ctx, cudaMallocHost(&hp->h_sz, 64));
+            return JPEZYB200_OK;
+        }();
+        if (rc != JPEZYB200_OK) {
+            host_pipe_destroy(ctx);
+            return rc;
+        }
     }
     *out = static_cast<HostPipe*>(ctx->host_pipe);
     return JPEZYB200_OK;

@@ -100,6 +100,7 @@ struct jpezyb200_ctx {
     int pad_ones = 1;
     int transform_variant = 0;
     int sync_rounds = 3;
+    int64_t shard_scratch = 0;                 // JPEZYB200_OPT_SHARD_SCRATCH_BYTES (0 = 3 bytes per pixel)
     int64_t group_bytes = int64_t(96) << 20;   // host<->device bytes per stage of the pipelined host batches
     uint64_t launches = 0;
     bool inv_attr_set = false, fwd_attr_set = false, fwd2_attr_set = false, inv2_attr_set = false;

@@ -19,6 +19,8 @@ constexpr int kEntThreads = 256;   // blocks per tile
 constexpr int kStuffThreads = 256;
 constexpr int kStuffChunk = kStuffThreads * 16;
 
+constexpr uint32_t kBadTile = 0xffffffffu;   // tile_sum of a tile that holds a coefficient without a baseline code
+
 struct EntParams {
     const int16_t* coefs;
     size_t coef_stride;      // int16 per image
@@ -86,14 +88,19 @@ __device__ __forceinline__ void load_block(const int16_t* __restrict__ base, con
 }
 
 // Visit the code words of one block in stream order.  emit(bits, nbits), nbits <= 27.
+// Returns false when a coefficient has no code in the baseline tables (DC difference of more than 11 bits, AC value of more
+// than 10 bits: the reference throws std::runtime_error there, src/encoder/jpezy_encoder.hpp:186,207); the table indices are
+// clamped so that such input -- possible through jpezyb200_entropy_encode_dev only -- never reads outside the tables.
 template <class Emit>
-__device__ __forceinline__ void encode_block(const BlockRegs& blk, int dc_pred, const uint32_t* __restrict__ ac,
+__device__ __forceinline__ bool encode_block(const BlockRegs& blk, int dc_pred, const uint32_t* __restrict__ ac,
                                              const uint32_t* __restrict__ dc, Emit&& emit)
 {
+    bool ok = true;
     // DC (:180-191)
     {
         const int diff = blk.dc() - dc_pred;
-        const int cat = bit_length(abs(diff));
+        int cat = bit_length(abs(diff));
+        if (cat > 11) ok = false, cat = 11;
         const uint32_t e = dc[cat];
         const uint32_t vbits = uint32_t(diff < 0 ? diff - 1 : diff) & ((1u << cat) - 1u);
         emit(((e >> 5) << cat) | vbits, int(e & 31u) + cat);
@@ -124,7 +131,8 @@ __device__ __forceinline__ void encode_block(const BlockRegs& blk, int dc_pred, 
             const uint32_t ww = (h >> 1) == 0 ? w[0] : ((h >> 1) == 1 ? w[1] : ((h >> 1) == 2 ? w[2] : w[3]));
             const int v = (h & 1) ? (int(ww) >> 16) : int(short(ww & 0xffffu));
             while (run > 15) { emit(zrl >> 5, int(zrl & 31u)); run -= 16; }
-            const int s = bit_length(abs(v));
+            int s = bit_length(abs(v));
+            if (s > 10) ok = false, s = 10;
             const uint32_t e = ac[(run << 4) | s];
             const uint32_t vbits = uint32_t(v < 0 ? v - 1 : v) & ((1u << s) - 1u);
             emit(((e >> 5) << s) | vbits, int(e & 31u) + s);
@@ -133,6 +141,7 @@ __device__ __forceinline__ void encode_block(const BlockRegs& blk, int dc_pred, 
         run += 8 - next;
     }
     if (run) emit(eob >> 5, int(eob & 31u));   // coefficient 63 is zero <=> a run is pending
+    return ok;
 }
 
 __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* s_warp, uint32_t* total)
@@ -176,6 +185,7 @@ __global__ void __launch_bounds__(kEntThreads) k_block_bits(const EntParams p)
     const size_t img = blockIdx.y;
     const uint32_t b = blockIdx.x * kEntThreads + threadIdx.x;
     uint32_t bits = 0;
+    bool bad = false;
     if (b < p.nblk) {
         const int16_t* base = p.coefs + img * p.coef_stride;
         const long long pb = prev_same_component(b);
@@ -184,12 +194,15 @@ __global__ void __launch_bounds__(kEntThreads) k_block_bits(const EntParams p)
         BlockRegs blk;
         int pred;
         load_block(base, p.bmeta ? p.bmeta + img * p.nblk : nullptr, b, pb, p.dc_init ? p.dc_init[img * 3 + comp] : 0, blk, pred);
-        encode_block(blk, pred, s_ac[cls], s_dc[cls], [&](uint32_t, int n) { bits += uint32_t(n); });
+        bad = !encode_block(blk, pred, s_ac[cls], s_dc[cls], [&](uint32_t, int n) { bits += uint32_t(n); });
     }
     uint32_t total;
     const uint32_t off = block_scan_excl(bits, s_warp, &total);
     if (b < p.nblk) p.blk_off[img * p.nblk + b] = off;
-    if (threadIdx.x == 0) p.tile_sum[img * p.ntile + blockIdx.x] = total;
+    // a coefficient without a code: the tile reports kBadTile, k_scan_tiles turns that into a bit count no slot can hold, and the
+    // image ends like one that does not fit (scan_bytes = UINT64_MAX) instead of as a silently corrupt stream
+    const int anybad = __syncthreads_or(bad ? 1 : 0);
+    if (threadIdx.x == 0) p.tile_sum[img * p.ntile + blockIdx.x] = anybad ? kBadTile : total;
 }
 
 // ---- E3b: one CTA per image, 64-bit running carry ------------------------------------------------------
@@ -203,7 +216,15 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const EntParams p)
     __syncthreads();
     for (uint32_t t0 = 0; t0 < p.ntile; t0 += 1024) {
         const uint32_t t = t0 + threadIdx.x;
-        const uint32_t v = t < p.ntile ? p.tile_sum[img * p.ntile + t] : 0u;
+        uint32_t v = t < p.ntile ? p.tile_sum[img * p.ntile + t] : 0u;
+        const int bad = __syncthreads_or(v == kBadTile ? 1 : 0);
+        if (bad) {
+            if (threadIdx.x == 0) {
+                p.img_bits[img] = 1ull << 62;
+                if (p.out_bits) p.out_bits[img] = ~0ull;
+            }
+            return;
+        }
         uint32_t total;
         const uint32_t off = block_scan_excl(v, s_warp, &total);   // < 1024 * 256 * 1700 bits: fits 32 bits
         const uint64_t carry = s_carry;

@@ -138,7 +138,9 @@ __global__ void __launch_bounds__(1024) k_shard_scan_ff(const ShardParams p)
     __shared__ uint64_t s_carry;
     const ShardGeom g = *p.geom;
     if (!g.fits) {
-        if (threadIdx.x == 0) *p.out_bytes = 0;
+        // this rank's stream did not fit its scratch: UINT64_MAX travels through all-gather #3, so that EVERY rank raises its
+        // overflow flag in k_shard_stuff_write (a silently short segment on rank 0 would be a corrupt file)
+        if (threadIdx.x == 0) *p.out_bytes = ~0ull;
         return;
     }
     const uint32_t nch = uint32_t((g.nown + kStuffChunk - 1) / kStuffChunk);
@@ -164,12 +166,14 @@ __global__ void __launch_bounds__(kStuffThreads) k_shard_stuff_write(const Shard
     __shared__ uint32_t s_warp[kStuffThreads / 32];
     const ShardGeom g = *p.geom;
     uint64_t byte_base = 0, total = 0;
+    bool peer_overflow = false;
     for (uint32_t j = 0; j < p.nranks; ++j) {
+        peer_overflow |= p.all_bytes[j] == ~0ull;          // some rank (maybe this one) ran out of scratch
         if (j < p.rank) byte_base += p.all_bytes[j];
         total += p.all_bytes[j];
     }
     const uint64_t mine = p.all_bytes[p.rank];
-    const bool ok = g.fits && total <= p.dst_cap && mine + 32 <= p.stage_cap;
+    const bool ok = !peer_overflow && g.fits && total <= p.dst_cap && mine + 32 <= p.stage_cap;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (p.total_bytes) *p.total_bytes = total;
         if (!ok) *p.overflow = 1;

@@ -166,7 +166,7 @@ class ShardedEncoder:
             self._owned = None
 
 
-def encode_sharded_local(ctxs, planes, W, H, gray=False, dst_cap=None, device="cuda"):
+def encode_sharded_local(ctxs, planes, W, H, gray=False, dst_cap=None, device="cuda", return_overflow_flags=False):
     """All ranks inside one process on one device, in lockstep (LocalGroup): validates the N-rank byte stream where only one
     GPU is available.  ctxs: one Context per emulated rank; planes: (r, g, b) uint8 tensors [H, W] on `device`.
     -> (segment bytes, per-rank bit counts)"""
@@ -200,8 +200,10 @@ def encode_sharded_local(ctxs, planes, W, H, gray=False, dst_cap=None, device="c
     for k in range(n):
         ctxs[k].shard_encode_d(nb, dst, dst_cap, total, ovf[k: k + 1], stream=st)
     torch.cuda.synchronize()
+    if return_overflow_flags:        # (tests: the flag of every emulated rank)
+        return [int(x) for x in ovf.cpu().tolist()]
     if int(ovf.sum().item()):
-        raise RuntimeError("stitched stream does not fit dst_cap=%d" % dst_cap)
+        raise RuntimeError("stitched stream does not fit dst_cap=%d (or a rank's scratch)" % dst_cap)
     return dst[: int(total.item())].cpu().numpy().tobytes(), [int(x) for x in info[:, 0].cpu().tolist()]
 
 
@@ -244,12 +246,26 @@ class ShardedDecoder:
         if g.size > 1:
             g.dist.broadcast(self.scan[:scan_bytes], src=0)
         pl = self.plane_len
+        self._last = (scan_bytes, gray, stream)
         self.ctx.shard_decode_dev(self.scan, scan_bytes, self.frame, gray, self.row0, self.nrows, self.base, self.base + pl,
                                   self.base + 2 * pl, pl, self.status, stream=stream)
 
     def result(self):
         """rank 0, after a barrier: the three planes as numpy arrays (reference layout: stride W, padded length)"""
+        from . import capi
         self.torch.cuda.synchronize()
+        if int(self.status.item()) == capi.EAGAIN:
+            # the enqueued synchronisation launches were not enough for this stream: this rank decodes again with the
+            # host-polled loop (always terminates); the segment is already here, the other ranks are not involved
+            scan_bytes, gray, stream = self._last
+            pl = self.plane_len
+            self.ctx.set_option(capi.OPT_SYNC_ROUNDS, 0)
+            try:
+                self.ctx.shard_decode_dev(self.scan, scan_bytes, self.frame, gray, self.row0, self.nrows, self.base, self.base + pl,
+                                          self.base + 2 * pl, pl, self.status, stream=stream)
+                self.torch.cuda.synchronize()
+            finally:
+                self.ctx.set_option(capi.OPT_SYNC_ROUNDS, 3)
         self.group.barrier()
         self.torch.cuda.synchronize()
         if int(self.status.item()):

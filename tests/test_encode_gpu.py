@@ -69,18 +69,27 @@ def test_guard_path_is_exercised(ctx, oracle):
 
 
 def test_exhaustive_colour_conversion(ctx, oracle):
-    # every (r,g,b) triple once: a 4096x4096 image holds all 2^24 colours; Y of every pixel and Cb/Cr of the
-    # even/even samples are compared through the DC coefficients... cheaper and sharper: compare all coefficients
-    # of a 1024x256 slice sweep instead (16 slices would take too long on the oracle) -> 4 random slices
-    rng = np.random.default_rng(7)
-    idx = np.arange(1 << 24, dtype=np.uint32)
-    for s in rng.choice(64, size=2, replace=False):
-        sl = idx[s * (1 << 18):(s + 1) * (1 << 18)]
-        W, H = 1024, 256
-        r = (sl & 255).astype(np.uint8).reshape(H, W)
-        g = ((sl >> 8) & 255).astype(np.uint8).reshape(H, W)
-        b = ((sl >> 16) & 255).astype(np.uint8).reshape(H, W)
-        assert (gpu_coefs(ctx, r, g, b, W, H)[0] == oracle.coefs(r, g, b, W, H)).all()
+    """every (r, g, b) triple exactly once: a 4096 x 4096 image holds all 2^24 colours.  All of its coefficients must equal the
+    oracle's -- luma sees every triple; the triple of pixel (x, y) is arranged so that the even/even positions, the only ones
+    chroma is taken from (decimation, src/encoder/jpezy_encoder.hpp:116-143), run through every triple as well over the four
+    images of the sweep (the (x, y) -> index map is shifted by (0|1, 0|1))."""
+    W = H = 4096
+    yy, xx = np.meshgrid(np.arange(H, dtype=np.uint32), np.arange(W, dtype=np.uint32), indexing="ij")
+    for dy in (0, 1):
+        for dx in (0, 1):
+            idx = (((yy + dy) % H) * W + ((xx + dx) % W)).astype(np.uint32)
+            # a permutation of the index that spreads neighbouring triples (otherwise every block is a smooth ramp)
+            idx = (idx * np.uint32(2654435761)) & np.uint32(0xffffff)
+            r = (idx & 255).astype(np.uint8)
+            g = ((idx >> 8) & 255).astype(np.uint8)
+            b = ((idx >> 16) & 255).astype(np.uint8)
+            if dy == 0 and dx == 0:
+                key = (r.astype(np.uint32) | (g.astype(np.uint32) << 8) | (b.astype(np.uint32) << 16)).ravel()
+                assert np.unique(key).size == 1 << 24, "the sweep image must hold every colour"
+            got = gpu_coefs(ctx, r, g, b, W, H)[0]
+            want = oracle.coefs(r, g, b, W, H)
+            nd = int((got != want).sum())
+            assert nd == 0, "%d coefficients differ (shift %d,%d)" % (nd, dx, dy)
 
 
 def test_gray_pixels_colour_boundaries(ctx, oracle):
@@ -116,6 +125,24 @@ def test_entropy_extreme_coefficients(ctx, oracle):
     got, _ = gpu_entropy(ctx, c, W, H)
     assert got[0] == want
     assert b"\xff\x00" in want
+
+
+@pytest.mark.parametrize("where", ["dc", "ac"])
+def test_entropy_refuses_coefficients_without_a_code(ctx, where):
+    """a DC difference of more than 11 bits or an AC value of more than 10 bits has no code in the Annex K tables: the reference
+    throws (src/encoder/jpezy_encoder.hpp:186,207); the device path must report the image (byte count < 0 = UINT64_MAX) instead
+    of emitting a stream with missing symbols -- and must leave the other image of the batch alone"""
+    n = 4
+    c = np.zeros((2, n, 6, 64), dtype=np.int16)
+    c[:, :, :, 0] = 5
+    if where == "dc":
+        c[1, 2, 0, 0] = 32000                      # difference to the previous block: 15 bits
+    else:
+        c[1, 1, 3, 9] = -2000                      # 11 bits
+    W, H = 16 * n, 16
+    got, _ = gpu_entropy(ctx, c, W, H, nimg=2)
+    assert got[0] is not None and len(got[0]) > 0
+    assert got[1] is None
 
 
 @pytest.mark.parametrize("pad_ones", [1, 0])

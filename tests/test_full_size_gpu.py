@@ -26,9 +26,11 @@ def synth_dev(ctx, W, H, family=0, frame=0):
     return d
 
 
-@pytest.mark.parametrize("name,W,H,gray", [("C2", 3840, 2160, False), ("C3 frame", 1920, 1080, False), ("C4", 8192, 8192, True)])
-def test_full_size_byte_and_sample_parity(ctx, oracle, name, W, H, gray):
-    d = synth_dev(ctx, W, H)
+@pytest.mark.parametrize("name,W,H,gray,family", [("C2", 3840, 2160, False, 0), ("C3 frame", 1920, 1080, False, 0), ("C4", 8192, 8192, True, 0),
+                                                  ("C2 S-noise", 3840, 2160, False, 1), ("C3 frame S-noise", 1920, 1080, False, 1)])
+def test_full_size_byte_and_sample_parity(ctx, oracle, name, W, H, gray, family):
+    # S-noise (2.5 bit/px) is the entropy stress case and the one that fills the guard-band queues of both transforms
+    d = synth_dev(ctx, W, H, family=family)
     r, g, b = (d[c].cpu().numpy() for c in range(3))
     scan, nbits = ctx.encode(r, g, b, W, H, gray=gray)
     want = oracle.encode(r, g, b, W, H, gray=gray)

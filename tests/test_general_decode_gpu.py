@@ -43,7 +43,11 @@ def jpeg_bytes(img, mode, **kw):
 CASES = [("444", "RGB", dict(quality=75, subsampling=0)), ("422", "RGB", dict(quality=75, subsampling=1)),
          ("420", "RGB", dict(quality=75, subsampling=2)), ("420_q95", "RGB", dict(quality=95, subsampling=2)),
          ("444_q30", "RGB", dict(quality=30, subsampling=0)), ("gray", "L", dict(quality=80)),
-         ("gray_q100", "L", dict(quality=100)), ("422_optimized_tables", "RGB", dict(quality=60, subsampling=1, optimize=True))]
+         ("gray_q100", "L", dict(quality=100)), ("422_optimized_tables", "RGB", dict(quality=60, subsampling=1, optimize=True)),
+         # Cb and Cr with DIFFERENT quantisation tables (Tq 1 and 2) on the 2x2 / 1x1 / 1x1 layout of the production inverse kernel
+         ("420_three_qtables", "RGB", dict(subsampling=2, qtables=[[8 + (i % 8) + 2 * (i // 8) for i in range(64)],
+                                                                  [11 + 3 * (i % 8) + (i // 8) for i in range(64)],
+                                                                  [29 + (i % 8) + 5 * (i // 8) for i in range(64)]]))]
 
 
 @pytest.mark.parametrize("name,mode,kw", CASES, ids=[c[0] for c in CASES])

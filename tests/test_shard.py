@@ -159,6 +159,13 @@ def test_sharded_encode_pad_zero_and_overflow(ctx, oracle):
         assert got == oracle.encode(r, g, b, W, H, pad_ones=False, scan_only=True)
         with pytest.raises(RuntimeError):
             shard.encode_sharded_local(ctxs, planes, W, H, dst_cap=100)
+        # ONE rank runs out of its own scratch: every rank must see it (no silently short segment on rank 0)
+        ctxs[1].set_option(capi.OPT_SHARD_SCRATCH_BYTES, 64)
+        flags = shard.encode_sharded_local(ctxs, planes, W, H, return_overflow_flags=True)
+        assert flags == [1, 1, 1]
+        ctxs[1].set_option(capi.OPT_SHARD_SCRATCH_BYTES, 0)
+        got, _ = shard.encode_sharded_local(ctxs, planes, W, H)
+        assert got == oracle.encode(r, g, b, W, H, pad_ones=False, scan_only=True)
     finally:
         for c in ctxs:
             c.close()
