@@ -351,6 +351,8 @@ static int launch_fwd_kernel(jpezyb200_ctx* ctx, const FwdParams& p, uint32_t ni
         ts.dimg = grid / per_img;
         ts.dmy = (grid % per_img) / tpr;
         ts.dbx = (grid % per_img) % tpr;
+        static const uint32_t tsflags = [] { const char* e = std::getenv("JPEZY_B200_FWD_FLAGS"); return e ? uint32_t(std::atoi(e)) : 0u; }();
+        ts.flags = tsflags;
         if (v == 0) (void)jz_launch(k_fwd_transform2<8, 3>, dim3(grid), dim3(Fwd2<8, 3>::kThreads), Fwd2<8, 3>::kSmem, st, p, ntiles, ts);
         else if (v == 1) (void)jz_launch(k_fwd_transform2<8, 2>, dim3(grid), dim3(Fwd2<8, 2>::kThreads), Fwd2<8, 2>::kSmem, st, p, ntiles, ts);
         else (void)jz_launch(k_fwd_transform2<16, 2>, dim3(grid), dim3(Fwd2<16, 2>::kThreads), Fwd2<16, 2>::kSmem, st, p, ntiles, ts);

@@ -293,6 +293,7 @@ struct Fwd2 {
 // How the tile ids advance from one tile of a CTA to its next (id += gridDim.x), precomputed on the host: no divisions in the loop
 struct TileStep {
     uint32_t tiles_per_row, dimg, dmy, dbx;
+    uint32_t flags;      // experiments: bit 0 = the DMA warp issues a tile's bulk copies from one lane instead of 32
 };
 
 // Persistent, warp-specialised CTAs.  CTA b transforms tiles b, b + gridDim.x, ... (a tile = T MCUs of one MCU row of one image).
@@ -317,7 +318,6 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
         mbar_init(bar_out_empty, 1), mbar_init(bar_out_empty + 8u, 1);
         mbar_fence_init();
     }
-    for (uint32_t i = t; i < sizeof(Q2Tab) / 4; i += C::kThreads) sts32(sm + C::oTab + 4u * i, reinterpret_cast<const uint32_t*>(&gQ2)[i]);
     if (t < 16) sts32(sm + C::oCnt + 4u * t, 0u);
     __syncthreads();
     pdl_wait();
@@ -340,20 +340,31 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
 
     if (warp == C::kWarps) {
         // ================= DMA warp =================
-        if (lane != 0) return;
+        // all 32 lanes issue the bulk copies of a tile (one per pixel row and plane: 48 requests in two rounds); lane 0 alone
+        // arms the barrier and sends the finished tiles off
         uint32_t limg = img, lmy = my, lbx = bx;       // next tile to load
         uint32_t lid = blockIdx.x;
         auto issue = [&](int st) {
             const uint32_t mx0 = lbx * T, nvalid = min(uint32_t(T), p.HU - mx0), gy0 = (p.row0 + lmy) * 16u;
             const uint32_t nrow = min(16u, p.H - gy0), rowbytes = nvalid * 16u, bar = bar_in_full + 8u * st;
-            mbar_expect_tx(bar, 3u * nrow * rowbytes);
+            if (lane == 0) mbar_expect_tx(bar, 3u * nrow * rowbytes);
+            __syncwarp();
             const size_t off = size_t(limg) * p.plane_stride + size_t(gy0 - p.y_origin) * p.W + size_t(mx0) * 16u;
             const uint32_t dst = sm + C::oIn + st * C::kIn;
+            if (ts.flags & 1u) {
+                if (lane == 0)
 #pragma unroll 1
-            for (uint32_t row = 0; row < nrow; ++row) {
-                bulk_g2s(dst + row * C::kRow, p.r + off + size_t(row) * p.W, rowbytes, bar);
-                bulk_g2s(dst + (16 + row) * C::kRow, p.g + off + size_t(row) * p.W, rowbytes, bar);
-                bulk_g2s(dst + (32 + row) * C::kRow, p.b + off + size_t(row) * p.W, rowbytes, bar);
+                    for (uint32_t row = 0; row < nrow; ++row) {
+                        bulk_g2s(dst + row * C::kRow, p.r + off + size_t(row) * p.W, rowbytes, bar);
+                        bulk_g2s(dst + (16 + row) * C::kRow, p.g + off + size_t(row) * p.W, rowbytes, bar);
+                        bulk_g2s(dst + (32 + row) * C::kRow, p.b + off + size_t(row) * p.W, rowbytes, bar);
+                    }
+            } else {
+#pragma unroll
+                for (int c = lane; c < 48; c += 32) {
+                    const uint32_t plane = uint32_t(c) >> 4, row = uint32_t(c) & 15u;
+                    if (row < nrow) bulk_g2s(dst + uint32_t(c) * C::kRow, (plane == 0 ? p.r : (plane == 1 ? p.g : p.b)) + off + size_t(row) * p.W, rowbytes, bar);
+                }
             }
             advance(limg, lmy, lbx);
             lid += gridDim.x;
@@ -370,20 +381,25 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
                 issue(lst);
                 lst = lst + 1 == NST ? 0 : lst + 1;
             }
-            const uint32_t ob = i & 1u;
-            mbar_wait_wd(bar_out_full + 8u * ob, (i >> 1) & 1u);
-            const uint32_t mx0 = bx * T, nvalid = min(uint32_t(T), p.HU - mx0);
-            bulk_s2g(p.coefs + size_t(img) * p.coef_stride + (size_t(my) * p.HU + mx0) * 384, sm + C::oOut + ob * C::kOut, nvalid * 768u);
-            bulk_commit();
-            bulk_wait_read0();                           // the store has read the staging buffer (not: has reached memory)
-            mbar_arrive(bar_out_empty + 8u * ob);
+            if (lane == 0) {
+                const uint32_t ob = i & 1u;
+                mbar_wait_wd(bar_out_full + 8u * ob, (i >> 1) & 1u);
+                const uint32_t mx0 = bx * T, nvalid = min(uint32_t(T), p.HU - mx0);
+                bulk_s2g(p.coefs + size_t(img) * p.coef_stride + (size_t(my) * p.HU + mx0) * 384, sm + C::oOut + ob * C::kOut, nvalid * 768u);
+                bulk_commit();
+                bulk_wait_read0();                           // the store has read the staging buffer (not: has reached memory)
+                mbar_arrive(bar_out_empty + 8u * ob);
+            }
+            __syncwarp();
             advance(img, my, bx);
         }
-        bulk_wait_read0();
         return;
     }
 
     // ================= compute warps =================
+    // the quantisation constants come to shared memory while the first tile is in flight (a barrier of the compute warps only)
+    for (uint32_t i = t; i < sizeof(Q2Tab) / 4; i += C::kWarps * 32) sts32(sm + C::oTab + 4u * i, reinterpret_cast<const uint32_t*>(&gQ2)[i]);
+    asm volatile("bar.sync 1, %0;" ::"r"(C::kWarps * 32) : "memory");
     const uint32_t pr = uint32_t(t) >> 3, sub = uint32_t(t) & 7u;    // block pair, row (phase 1) / column (phase 2)
     const bool luma = pr < 2u * T;                                   // warp uniform (4 pairs per warp)
     const uint32_t mcu = luma ? (pr >> 1) : pr - 2u * T;

@@ -1,0 +1,74 @@
+"""-m gpu: compute-sanitizer is closed on this pool (profiles/r02_sanitizer_closed.log), so the out-of-bounds check is our
+own: every output buffer of the device-resident entry points sits between two poisoned guard zones, which must come back
+untouched, and inputs sit at the very end of their allocation's used part (a read past the end lands in the next guard)."""
+import numpy as np
+import pytest
+import torch
+
+import jpezy_b200 as J
+from jpezy_b200 import capi
+
+pytestmark = pytest.mark.gpu
+GUARD = 4096
+
+
+class Guarded:
+    """n bytes of `dtype` elements with GUARD poisoned bytes on either side (the payload stays 256-byte aligned)"""
+    def __init__(self, nelem, dtype, fill=0):
+        self.esz = torch.empty(0, dtype=dtype).element_size()
+        self.n = nelem * self.esz
+        self.raw = torch.full((GUARD + self.n + GUARD,), 0xA5, dtype=torch.uint8, device="cuda")
+        self.view = self.raw[GUARD: GUARD + self.n].view(dtype)
+        self.view.fill_(fill)
+
+    def intact(self):
+        return bool((self.raw[:GUARD] == 0xA5).all().item()) and bool((self.raw[GUARD + self.n:] == 0xA5).all().item())
+
+
+@pytest.mark.parametrize("W,H,family,gray,nimg", [(208, 128, 0, False, 1), (1920, 1080, 0, False, 2), (200, 120, 1, False, 3),
+                                                   (17, 33, 2, True, 1), (3840, 2160, 1, False, 1), (16, 16, 0, False, 5),
+                                                   (4080, 16, 0, False, 1), (136, 1088, 1, True, 2)])
+def test_device_entry_points_stay_inside_their_buffers(ctx, W, H, family, gray, nimg):
+    npx = W * H
+    frame = J.default_frame(W, H)
+    pl = capi.plane_bytes(frame)
+    nm = capi.num_mcus(W, H)
+    slot = max(3 * npx, 10240)
+    planes_in = [Guarded(nimg * npx, torch.uint8) for _ in range(3)]
+    coefs = Guarded(nimg * nm * 384, torch.int16, fill=0x7777)
+    scan = Guarded(nimg * slot, torch.uint8)
+    nbytes = Guarded(nimg, torch.int64)
+    nbits = Guarded(nimg, torch.int64)
+    status = Guarded(nimg, torch.int32, fill=-1)
+    out = [Guarded(nimg * pl, torch.uint8, fill=0x11) for _ in range(3)]
+    st = torch.cuda.Stream()
+    sp = st.cuda_stream
+    torch.cuda.synchronize()
+    with torch.cuda.stream(st):
+        ctx.synth_dev(planes_in[0].view, planes_in[1].view, planes_in[2].view, W, H, nimg=nimg, first_frame=3, family=family, stream=sp)
+        # per-stage entry points ...
+        ctx.transform_fwd_dev(planes_in[0].view, planes_in[1].view, planes_in[2].view, W, H, nimg, gray, coefs.view, stream=sp)
+        ctx.entropy_encode_dev(coefs.view, W, H, nimg, gray, scan.view, slot, nbytes.view, nbits.view, stream=sp)
+        torch.cuda.synchronize()
+        h_nb = nbytes.view.cpu().numpy().astype(np.uint64)
+        assert (nbytes.view > 0).all()
+        coefs2 = Guarded(nimg * nm * 384, torch.int16, fill=0x7777)
+        ctx.entropy_decode_dev(scan.view, slot, h_nb, nimg, frame, coefs2.view, status.view, stream=sp)
+        ctx.transform_inv_dev(coefs2.view, frame, nimg, gray, out[0].view, out[1].view, out[2].view, pl, stream=sp)
+        torch.cuda.synchronize()
+        assert (status.view == 0).all()
+        assert torch.equal(coefs.view, coefs2.view), "entropy decode does not invert entropy encode"
+        first = [o.view.clone() for o in out]
+        # ... and the fused ones, both length conventions
+        scan.view.zero_()
+        for o in out:
+            o.view.fill_(0x22)
+        ctx.encode_batch_dev(planes_in[0].view, planes_in[1].view, planes_in[2].view, W, H, nimg, gray, scan.view, slot, nbytes.view, nbits.view, stream=sp)
+        ctx.decode_batch_dev2(scan.view, slot, nbytes.view, int(h_nb.max()), nimg, frame, gray, out[0].view, out[1].view, out[2].view, pl, status.view, stream=sp)
+        torch.cuda.synchronize()
+    assert (status.view == 0).all()
+    for a, b in zip(first, out):
+        assert torch.equal(a, b.view), "fused and per-stage paths disagree"
+    for name, gbuf in [("planes_in", planes_in[0]), ("planes_in", planes_in[1]), ("planes_in", planes_in[2]), ("coefs", coefs), ("coefs2", coefs2),
+                       ("scan", scan), ("nbytes", nbytes), ("nbits", nbits), ("status", status), ("out", out[0]), ("out", out[1]), ("out", out[2])]:
+        assert gbuf.intact(), "guard zone around %s was written" % name

@@ -9,7 +9,10 @@ import jpezy_b200 as J
 from jpezy_b200 import shard
 
 ctx = J.Context(0)
-for fam, W, H, gray in ((0, 200, 120, False), (1, 64, 48, False), (2, 17, 33, True), (1, 640, 360, False), (0, 1, 1, False)):
+# (sizes with 16-byte aligned rows take the second-generation transform kernels -- TMA bulk copies, mbarriers, warp-specialised
+# pipeline --, the others the first-generation ones; S-noise fills the guard-band queues)
+for fam, W, H, gray in ((0, 208, 128, False), (1, 64, 48, False), (2, 17, 33, True), (1, 640, 360, False), (0, 1, 1, False),
+                        (0, 1920, 1080, False), (1, 320, 200, True)):
     r, g, b = J.synth.image(fam, W, H)
     scan, _ = ctx.encode(r, g, b, W, H, gray=gray)
     R, G, B = ctx.decode(scan, J.default_frame(W, H), gray=gray)
