@@ -33,6 +33,25 @@ WORKLOADS = {
 FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: everything else libraries print there (NCCL's version banner, ...)
+    is sent to stderr -- file descriptor 1 is pointed at stderr, the real one is kept for emit()"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -138,7 +157,7 @@ def run_reference(args, wl):
                              "encode_MPix_s_per_core": float(W) * rows * args.steps / te / 1e6 if te else None,
                              "decode_MPix_s_per_core": float(W) * rows * args.steps / td / 1e6 if td else None},
             "e2e": {"value": val, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_sharded(args, wl):
@@ -233,7 +252,7 @@ def run_sharded(args, wl):
                              "algorithmic_bytes_per_launch": alg, "ms_per_launch": t_fwd},
                 "cpu_baseline": None,
                 "stages": {"stream_bytes": len(seg), "bits_per_rank": bits, "fwd_transform_ms_rank0": t_fwd}}
-        print(json.dumps(line))
+        emit(line)
     enc.close()
     dist.destroy_process_group()
     ctx.close()
@@ -314,11 +333,193 @@ def run_sharded_gray(args, wl):
                                        "transform stage by MCU rows with P2P stores into rank 0"},
                 "clocks": sampler.summary(), "gpu_launches": int(launches), "e2e": None, "roofline": None, "cpu_baseline": None,
                 "stages": {"stream_bytes": n_scan, "decoded_ok": ok}}
-        print(json.dumps(line))
+        emit(line)
     dec.close()
     enc.close()
     dist.destroy_process_group()
     ctx.close()
+
+
+def extra_configs(args, ctx, dist, rank, local_rank, world):
+    """The other BASELINE.json configurations, measured in the same process right after the headline workload (a few steps
+    each; device-timed like the headline, max over ranks).  Returned on rank 0 as the `configs` object of the JSON line:
+      c3        batch of 1920x1080 frames, 64 per GPU, sharded by image (weak scaling, no data-path collective)
+      c5        ONE 32768x32768 image, encode sharded by MCU rows (strong scaling): total, the seven phases of the sharded
+                encoder (which all-gather or kernel limits it) and the SHA-256 of the stitched segment against the segment
+                rank 0 encodes alone from the same pixels
+      c4_shard  ONE 8192x8192 --gray image, encode + decode sharded by MCU rows; decoded planes against a single-GPU decode"""
+    import hashlib
+    import numpy as np
+    import torch
+    import jpezy_b200 as J
+    from jpezy_b200 import capi, shard
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    peak, _ = measured_peak()
+    out = {}
+    own_group = False
+    if dist is None:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
+        own_group = True
+
+    def rank_max(ms):
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(fn, warm, steps):
+        for i in range(warm):
+            fn(i)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(stream)
+        sync_all()
+        return rank_max(e0.elapsed_time(e1)) / steps
+
+    # ---- C3: batch by image ----
+    try:
+        W, H, B = 1920, 1080, 64
+        npx = W * H
+        frame = J.default_frame(W, H)
+        pl = J.plane_bytes(frame)
+        ring = 2                                                   # 2 x (398 + 398) MB of frames: far above the 126 MB L2
+        slot = npx
+        d_in = torch.empty((ring, 3, B, H, W), dtype=torch.uint8, device="cuda")
+        d_out = torch.zeros((ring, 3, B, pl), dtype=torch.uint8, device="cuda")
+        d_scan = torch.zeros((ring, B, slot), dtype=torch.uint8, device="cuda")
+        d_nb = torch.zeros((ring, B), dtype=torch.int64, device="cuda")
+        d_st = torch.zeros((ring, B), dtype=torch.int32, device="cuda")
+        d_coefs = torch.empty((B, capi.num_mcus(W, H), 6, 64), dtype=torch.int16, device="cuda")
+        for k in range(ring):
+            ctx.synth_dev(d_in[k, 0], d_in[k, 1], d_in[k, 2], W, H, nimg=B, first_frame=(rank * ring + k) * B, family=args.family, stream=sp)
+            ctx.encode_batch_dev(d_in[k, 0], d_in[k, 1], d_in[k, 2], W, H, B, False, d_scan[k], slot, d_nb[k], None, stream=sp)
+        torch.cuda.synchronize()
+        h_nb = d_nb.cpu().numpy().astype(np.uint64)
+        bound = min(slot, int(h_nb.max() * 1.25) + 4096)
+
+        def step(i):
+            k = i % ring
+            ctx.encode_batch_dev(d_in[k, 0], d_in[k, 1], d_in[k, 2], W, H, B, False, d_scan[k], slot, d_nb[k], None, stream=sp)
+            ctx.decode_batch_dev2(d_scan[k], slot, d_nb[k], bound, B, frame, False, d_out[k, 0], d_out[k, 1], d_out[k, 2], pl, d_st[k], stream=sp)
+        ms = timed_loop(step, 3, 10)
+        assert int(d_st.abs().sum().item()) == 0
+        t = {}
+        t["fwd_transform_ms"] = timed_loop(lambda i: ctx.transform_fwd_dev(d_in[i % ring, 0], d_in[i % ring, 1], d_in[i % ring, 2], W, H, B, False, d_coefs, stream=sp), 2, 8)
+        t["entropy_encode_ms"] = timed_loop(lambda i: ctx.entropy_encode_dev(d_coefs, W, H, B, False, d_scan[i % ring], slot, d_nb[i % ring], None, stream=sp), 2, 8)
+        t["entropy_decode_ms"] = timed_loop(lambda i: ctx.entropy_decode_dev(d_scan[i % ring], slot, h_nb[i % ring], B, frame, d_coefs, d_st[i % ring], stream=sp), 2, 8)
+        t["inv_transform_ms"] = timed_loop(lambda i: ctx.transform_inv_dev(d_coefs, frame, B, False, d_out[i % ring, 0], d_out[i % ring, 1], d_out[i % ring, 2], pl, stream=sp), 2, 8)
+        out["c3"] = {"workload": "batch of 1920x1080 RGB frames sharded by image", "batch_per_gpu": B, "n_gpus": world, "scaling": "weak",
+                     "value": world * B * npx / (ms * 1e-3) / 1e6, "unit": "MPix/s", "ms_per_step": ms, "steps": 10, "stages": t,
+                     "fwd_transform_frac_of_hbm": 6.0 * B * npx / (t["fwd_transform_ms"] * 1e-3) / 1e9 / peak,
+                     "inv_transform_frac_of_hbm": 6.0 * B * npx / (t["inv_transform_ms"] * 1e-3) / 1e9 / peak,
+                     "bits_per_pixel": float(h_nb.mean()) * 8 / npx}
+        del d_in, d_out, d_scan, d_coefs
+        torch.cuda.empty_cache()
+    except Exception as e:       # a configuration that cannot run here is reported, the headline line still prints
+        out["c3"] = {"error": repr(e)[:300]}
+
+    grp = shard.DistGroup(dist, torch.device("cuda", local_rank))
+
+    # ---- C5: one giant image, encode sharded by MCU rows ----
+    try:
+        W = H = 32768
+        VU = (H + 15) // 16
+        row0, nrows = shard.partition_mcu_rows(VU, world)[rank]
+        y0, ny = shard.pixel_rows(H, row0, nrows)
+        planes = torch.empty((3, ny, W), dtype=torch.uint8, device="cuda")
+        ctx.synth_rows_dev(planes[0], planes[1], planes[2], W, y0, ny, frame=0, family=args.family, stream=sp)
+        cap = W * H // 2
+        enc = shard.ShardedEncoder(ctx, grp, cap)
+        ms = timed_loop(lambda i: enc.encode(planes[0], planes[1], planes[2], W, H, row0, nrows, y0, False, stream=sp), 2, 5)
+        # the seven phases, three instrumented steps (each synchronised), max over ranks of the mean
+        enc.phase_events = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+        acc = None
+        for _ in range(3):
+            enc.encode(planes[0], planes[1], planes[2], W, H, row0, nrows, y0, False, stream=sp)
+            sync_all()
+            pm = enc.phase_ms()
+            acc = pm if acc is None else {k: acc[k] + v for k, v in pm.items()}
+        enc.phase_events = None
+        phases = {k: rank_max(v / 3) for k, v in acc.items()}
+        seg, bits = enc.result()
+        sha_sharded = hashlib.sha256(seg).hexdigest() if rank == 0 else None
+        sha_single = None
+        if rank == 0:
+            # the same pixels encoded by this GPU alone (the reference itself cannot: `int size = W*H*3` overflows, DESIGN.md 6)
+            del planes
+            torch.cuda.empty_cache()
+            full = torch.empty((3, H, W), dtype=torch.uint8, device="cuda")
+            ctx.synth_rows_dev(full[0], full[1], full[2], W, 0, H, frame=0, family=args.family, stream=sp)
+            one = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+            nb1 = torch.zeros(1, dtype=torch.int64, device="cuda")
+            ctx.encode_batch_dev(full[0], full[1], full[2], W, H, 1, False, one, cap, nb1, None, stream=sp)
+            torch.cuda.synchronize()
+            n1 = int(nb1.item())
+            sha_single = hashlib.sha256(one[:n1].cpu().numpy().tobytes()).hexdigest() if n1 > 0 else "overflow"
+            del full, one
+        dist.barrier()
+        enc.close()
+        out["c5"] = {"workload": "single 32768x32768 RGB image, encode split by MCU rows", "n_gpus": world, "scaling": "strong",
+                     "value": float(W) * H / (ms * 1e-3) / 1e6, "unit": "MPix/s (encode)", "ms_per_step": ms, "steps": 5,
+                     "phases_ms": phases, "stream_bytes": len(seg) if seg is not None else None,
+                     "sha256_sharded": sha_sharded, "sha256_single_gpu": sha_single,
+                     "byte_identical_to_single_gpu": (sha_sharded == sha_single) if rank == 0 else None}
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["c5"] = {"error": repr(e)[:300]}
+
+    # ---- C4 --shard: one 8192x8192 --gray image, encode + decode sharded by MCU rows ----
+    try:
+        W = H = 8192
+        row0, nrows = shard.partition_mcu_rows((H + 15) // 16, world)[rank]
+        y0, ny = shard.pixel_rows(H, row0, nrows)
+        planes = torch.empty((3, ny, W), dtype=torch.uint8, device="cuda")
+        ctx.synth_rows_dev(planes[0], planes[1], planes[2], W, y0, ny, frame=0, family=args.family, stream=sp)
+        cap = W * H // 2
+        frame = J.default_frame(W, H)
+        enc = shard.ShardedEncoder(ctx, grp, cap)
+        dec = shard.ShardedDecoder(ctx, grp, frame, cap)
+        enc.encode(planes[0], planes[1], planes[2], W, H, row0, nrows, y0, True, stream=sp)
+        seg, _ = enc.result()
+        nb = torch.zeros(1, dtype=torch.int64, device="cuda")
+        if rank == 0:
+            nb[0] = len(seg)
+            dec.scan[: len(seg)] = torch.frombuffer(bytearray(seg), dtype=torch.uint8).cuda()
+        dist.broadcast(nb, src=0)
+        n_scan = int(nb.item())
+
+        def step(i):
+            enc.encode(planes[0], planes[1], planes[2], W, H, row0, nrows, y0, True, stream=sp)
+            dec.decode(n_scan, True, stream=sp)
+        ms = timed_loop(step, 2, 8)
+        res = dec.result()
+        same = None
+        if rank == 0:
+            r1, g1, b1 = ctx.decode(seg, frame, gray=True)
+            same = bool((res[0] == r1).all() and (res[1] == g1).all() and (res[2] == b1).all())
+        dist.barrier()
+        dec.close()
+        enc.close()
+        out["c4_shard"] = {"workload": "--gray 8192x8192, ONE image, encode + decode sharded by MCU rows", "n_gpus": world, "scaling": "strong",
+                           "value": float(W) * H / (ms * 1e-3) / 1e6, "unit": "MPix/s", "ms_per_step": ms, "steps": 8, "stream_bytes": n_scan,
+                           "decode_entropy_stage": "replicated on every rank (segment broadcast from rank 0); transform stage sharded",
+                           "planes_identical_to_single_gpu_decode": same}
+    except Exception as e:
+        out["c4_shard"] = {"error": repr(e)[:300]}
+    if own_group:
+        dist.destroy_process_group()
+    return out
 
 
 def main():
@@ -336,8 +537,10 @@ def main():
     ap.add_argument("--shard", action="store_true", help="c4 under torchrun: ONE image split by MCU rows over the ranks (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the c3 / c5 / c4_shard measurements appended to the default line")
     ap.add_argument("--host-lengths", action="store_true", help="segment lengths through a host array between encoder and decoder (round-1 step)")
     args = ap.parse_args()
+    claim_stdout()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
         wl["batch"] = args.batch
@@ -678,6 +881,13 @@ def main():
                "encode_MPix_s": px / te1 / 1e6, "decode_MPix_s": px / td1 / 1e6,
                "all_cores": {"cores": cores, "value": px * cores / wallc / 1e6, "how": "one single-threaded instance per core"}}
 
+    # ---- the other BASELINE.json configurations (C3 by image, C5 / C4 by MCU rows), same process, same ranks ----
+    configs = None
+    if args.workload == "c2" and not args.no_configs:
+        del d_in, d_out, d_scan, d_coefs
+        torch.cuda.empty_cache()
+        configs = extra_configs(args, ctx, dist, rank, local_rank, world)
+
     if rank == 0:
         line = {"metric": "encode+decode MPix/s", "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -688,9 +898,9 @@ def main():
                                ring, ring * (in_bytes + out_bytes) / 1e6),
                            "sharding": "by image, no data-path collective"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "stages": stages, "roundtrip_psnr_db": psnr, "roundtrip_psnr_db_after_timed_loop": psnr_after,
+                "stages": stages, "configs": configs, "roundtrip_psnr_db": psnr, "roundtrip_psnr_db_after_timed_loop": psnr_after,
                 "segment_lengths": "host array (read back between encoder and decoder)" if args.host_lengths else "device memory (jpezyb200_decode_batch_dev2, sized for %d bytes per segment)" % bound[0]}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     ctx.close()

@@ -103,6 +103,7 @@ class ShardedEncoder:
         self.all_bytes = torch.zeros(n, dtype=torch.int64, device=dev)
         self.total = torch.zeros(1, dtype=torch.int64, device=dev)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.phase_events = None
         # the stitched stream lives on rank 0; the other ranks map it (CUDA IPC) and store into it over NVLink
         self._owned = self._mapped = None
         if group.size == 1:
@@ -124,14 +125,31 @@ class ShardedEncoder:
         if not stream:
             raise ValueError("ShardedEncoder.encode needs torch's current non-default stream (torch.cuda.Stream)")
         c, g = self.ctx, self.group
+        ev = self.phase_events          # None, or 8 CUDA events bracketing the seven phases (bench.py: which phase limits the scaling)
+        mark = (lambda k: ev[k].record()) if ev is not None else (lambda k: None)
+        mark(0)
         c.shard_encode_a(d_r, d_g, d_b, W, H, row0, nrows, y_origin, gray, self.last_dc, stream=stream)
+        mark(1)
         g.all_gather(self.all_dc, self.last_dc)
+        mark(2)
         dc_init = self.all_dc[g.rank - 1] if g.rank > 0 else self.zero_dc
         c.shard_encode_b(dc_init, self.info, stream=stream)
+        mark(3)
         g.all_gather(self.all_info, self.info)
+        mark(4)
         c.shard_encode_c(self.all_info, g.rank, g.size, self.nbytes, stream=stream)
+        mark(5)
         g.all_gather(self.all_bytes, self.nbytes)
+        mark(6)
         c.shard_encode_d(self.all_bytes, self.dst, self.dst_cap, self.total, self.overflow, stream=stream)
+        mark(7)
+
+    PHASES = ("a_transform_lastdc", "allgather1_dc", "b_bits_scatter", "allgather2_bits", "c_geometry_ffcount", "allgather3_bytes", "d_stuff_push")
+
+    def phase_ms(self):
+        """after a synchronise: duration of the seven phases of the last encode() made with phase_events set"""
+        ev = self.phase_events
+        return {name: ev[k].elapsed_time(ev[k + 1]) for k, name in enumerate(self.PHASES)}
 
     def result(self):
         """rank 0, after a barrier: (bytes of the stitched segment, per-rank bit counts).  Raises on overflow."""
