@@ -862,6 +862,46 @@ def main():
                "api": api + "; two-stage host pipeline: step i+1 is encoded (context 1, host thread 1) while step i is decoded "
                             "(context 2, host thread 2), every step with its own H2D and D2H copies",
                "one_call_after_the_other": {"value": v_seq, "unit": "MPix/s", "steps": n_e2e}}
+        # The ceiling of this figure on this host: the step's copies alone (its host-to-device bytes and its device-to-host
+        # bytes, pinned, in opposite directions at the same time on two streams, no kernels), all ranks at once.  A step can
+        # not be faster than its copies; e2e.frac_of_ceiling says how much of what the PCIe links / the host memory give is
+        # reached (tools/pcie_probe.py is the same measurement as a stand-alone probe).
+        try:
+            s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+            up_src = [t_.reshape(-1) for t_ in hin[0]]
+            up_dst = [torch.empty(x.numel(), dtype=torch.uint8, device="cuda") for x in up_src]
+            dn_dst = [t_.reshape(-1) for t_ in hout]
+            dn_src = [torch.empty(x.numel(), dtype=torch.uint8, device="cuda") for x in dn_dst]
+            n_probe = 10
+
+            def probe():
+                with torch.cuda.stream(s_up):
+                    for a_, b_ in zip(up_dst, up_src):
+                        a_.copy_(b_, non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    for a_, b_ in zip(dn_dst, dn_src):
+                        a_.copy_(b_, non_blocking=True)
+            for _ in range(2):
+                probe()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_probe):
+                probe()
+            torch.cuda.synchronize()
+            dt_probe = time.perf_counter() - t0
+            if dist is not None:
+                tp = torch.tensor([dt_probe], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+                dt_probe = float(tp.item())
+            ceil_v = world * B * npx * n_probe / dt_probe / 1e6
+            e2e["ceiling"] = {"value": ceil_v, "unit": "MPix/s",
+                              "how": "copies of one step only: %d B host-to-device and %d B device-to-host per rank, pinned, concurrently on two "
+                                     "streams, %d ranks at once" % (sum(x.numel() for x in up_src), sum(x.numel() for x in dn_dst), world),
+                              "h2d_GBs_per_rank": sum(x.numel() for x in up_src) * n_probe / dt_probe / 1e9,
+                              "d2h_GBs_per_rank": sum(x.numel() for x in dn_dst) * n_probe / dt_probe / 1e9}
+            e2e["frac_of_ceiling"] = v_pipe / ceil_v
+        except Exception as ex:
+            e2e["ceiling"] = {"error": repr(ex)[:200]}
 
     sampler.stop_flag = True
     clocks = sampler.summary()

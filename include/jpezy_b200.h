@@ -34,7 +34,7 @@ enum {
     JPEZYB200_EINVAL = 1,       /* bad argument (null pointer, zero size, > 65535)                 */
     JPEZYB200_ECAPACITY = 2,    /* output buffer too small (reference: bofstream overflow)         */
     JPEZYB200_ECUDA = 3,        /* CUDA runtime error, see jpezyb200_last_error                   */
-    JPEZYB200_ENCCL = 4,        /* collective error (multi-GPU paths)                              */
+    JPEZYB200_ENCCL = 4,        /* multi-GPU exchange impossible (jpezyb200_group_create: no peer access to rank 0) */
     JPEZYB200_ECORRUPT = 5,     /* entropy-coded segment cannot be decoded (reference: decode()
                                    returns an empty optional, src/decoder/jpezy_decoder.hpp:109-114) */
     JPEZYB200_ENODEVICE = 6,    /* no CUDA device: there is no CPU path                            */
@@ -240,6 +240,23 @@ JPEZYB200_API int jpezyb200_shard_encode_c(jpezyb200_ctx* ctx, const uint64_t* d
                              uint64_t* d_out_bytes, void* stream);
 JPEZYB200_API int jpezyb200_shard_encode_d(jpezyb200_ctx* ctx, const uint64_t* d_all_bytes, uint8_t* d_dst, size_t dst_cap,
                              uint64_t* d_total_bytes, int32_t* d_overflow, void* stream);
+
+/* The same from ONE host thread (a C or C++ host, as the reference is): a group owns one context per rank -- rank k on CUDA
+ * device devices[k]; naming a device more than once emulates several ranks on it -- runs the four phases on the ranks' streams
+ * and performs the three exchanges itself (peer copies of 12, 16 and 8 bytes ordered with events; no collective library, no
+ * host synchronisation before the end).  d_r[k] / d_g[k] / d_b[k]: device pointers on rank k's device holding the pixel rows
+ * of that rank's MCU rows (jpezyb200_group_partition: the same split as jpezy_b200/shard.py), row stride W.  The stitched
+ * segment lands in d_dst on rank 0's device; the other devices need peer access to it (JPEZYB200_ENCCL from group_create if
+ * the hardware refuses).  Blocking; *scan_bytes receives the segment length. */
+typedef struct jpezyb200_group jpezyb200_group;
+JPEZYB200_API int jpezyb200_group_create(int nranks, const int* devices, jpezyb200_group** out);
+JPEZYB200_API void jpezyb200_group_destroy(jpezyb200_group* g);
+JPEZYB200_API int jpezyb200_group_size(const jpezyb200_group* g);
+JPEZYB200_API const char* jpezyb200_group_last_error(const jpezyb200_group* g);
+JPEZYB200_API jpezyb200_ctx* jpezyb200_group_ctx(jpezyb200_group* g, uint32_t rank);
+JPEZYB200_API int jpezyb200_group_partition(const jpezyb200_group* g, uint32_t H, uint32_t rank, uint32_t* mcu_row0, uint32_t* mcu_rows);
+JPEZYB200_API int jpezyb200_group_encode(jpezyb200_group* g, const uint8_t* const* d_r, const uint8_t* const* d_g, const uint8_t* const* d_b,
+                           uint32_t W, uint32_t H, int gray, uint8_t* d_dst, size_t dst_cap, uint64_t* scan_bytes);
 
 /* One image decoded by several GPUs.  The restart-less entropy-coded segment is decoded whole on every rank (replicas:
  * its self-synchronising decoder is latency bound and a byte-range split would have to redistribute the coefficients by MCU

@@ -18,6 +18,8 @@ EXPORTS = [
     "jpezyb200_synth_dev", "jpezyb200_synth_rows_dev", "jpezyb200_shard_encode_a", "jpezyb200_shard_encode_b",
     "jpezyb200_shard_encode_c", "jpezyb200_shard_encode_d", "jpezyb200_ipc_alloc", "jpezyb200_ipc_open", "jpezyb200_ipc_close",
     "jpezyb200_ipc_free", "jpezyb200_shard_decode_dev", "jpezyb200_encode_batch", "jpezyb200_decode_batch", "jpezyb200_read_sizes",
+    "jpezyb200_group_create", "jpezyb200_group_destroy", "jpezyb200_group_size", "jpezyb200_group_last_error", "jpezyb200_group_ctx",
+    "jpezyb200_group_partition", "jpezyb200_group_encode",
 ]
 
 

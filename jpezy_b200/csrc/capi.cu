@@ -583,3 +583,4 @@ int jpezyb200_synth_rows_dev(jpezyb200_ctx* ctx, uint8_t* d_r, uint8_t* d_g, uin
 #include "capi_decode.inc"
 #include "capi_shard.inc"
 #include "capi_batch.inc"
+#include "capi_group.inc"
