@@ -77,7 +77,7 @@ int main(int argc, char** argv)
     }
     // a destination that is too small must be reported, not overrun
     uint64_t dummy = 0;
-    CHECK(jpezyb200_group_encode(g, pr.data(), pg.data(), pb.data(), W, H, gray, dst, 64, &dummy) == JPEZYB200_ECAPACITY);
+    CHECK(jpezyb200_group_encode(g, pr.data(), pg.data(), pb.data(), W, H, gray, dst, 1, &dummy) == JPEZYB200_ECAPACITY);
     std::printf("group_encode ok: %ux%u, %d ranks, %llu bytes, identical to the single-GPU segment\n", W, H, n, (unsigned long long)n_one);
     jpezyb200_group_destroy(g);
     for (uint8_t* p : owned) cudaFree(p);
