@@ -79,7 +79,8 @@ def main():
         pass
     print(json.dumps({"stage": a.stage, "W": W, "H": H, "batch": B, "family": a.family, "gray": gray, "variant": a.variant,
                       "tile": os.environ.get("JPEZY_B200_FWD_TILE", ""), "us_per_launch": round(us, 2), "GBs": round(gbs, 1),
-                      "frac_of_measured_peak": round(gbs / peak, 4), "guard_fwd": ctx.stat(capi.STAT_GUARD_FWD)}))
+                      "frac_of_measured_peak": round(gbs / peak, 4), "guard_fwd": ctx.stat(capi.STAT_GUARD_FWD),
+                      "sync_iters": [ctx.stat(capi.STAT_SYNC_ITERS0), ctx.stat(capi.STAT_SYNC_ITERS1)], "sync_rounds": ctx.stat(capi.STAT_SYNC_ROUNDS)}))
 
 
 if __name__ == "__main__":
