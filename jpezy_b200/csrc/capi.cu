@@ -150,8 +150,8 @@ int jpezyb200_ctx_create(int device, jpezyb200_ctx** out)
                         float K = qc.K[c][i * 8 + j];
                         if ((i | j) == 0) K = float((1.0 - 1.0 / 1048576.0) / (8.0 * (c ? kQuantChroma[0] : kQuantLuma[0])));
                         else gmax = std::max(gmax, double(qc.G[c][i * 8 + j]));
-                        q2.K[c][j][i] = make_float2(K, K);
-                        q2.G[c][j][i] = qc.G[c][i * 8 + j];
+                        q2.K[c][i >> 1][j][i & 1] = make_float2(K, K);
+                        q2.G[c][i][j] = qc.G[c][i * 8 + j];
                     }
                 const float thr = float(1.0 - 2.0 * gmax);
                 std::memcpy(&q2.thr[c], &thr, 4);
@@ -325,18 +325,20 @@ static int launch_fwd_kernel(jpezyb200_ctx* ctx, const FwdParams& p, uint32_t ni
         k_fwd_transform_f64<<<grid, kFwdThreads, 0, st>>>(p);
     } else if (ctx->transform_variant == 0 && fwd2_ok(p)) {
         // second-generation kernel: persistent CTAs, rows fetched by bulk copies (needs 16-byte aligned rows and buffers)
-        static const int cfg = [] { const char* e = std::getenv("JPEZY_B200_FWD_CFG"); return e ? std::atoi(e) : 83; }();   // tile MCUs * 10 + stages
+        // JPEZY_B200_FWD_CFG (tuning runs): 83 = the compute warps store their own blocks (default), 82 = the DMA warp stores whole tiles,
+        // 84 = as 83 with four input stages
+        static const int cfg = [] { const char* e = std::getenv("JPEZY_B200_FWD_CFG"); return e ? std::atoi(e) : 83; }();
         if (!ctx->fwd2_attr_set) {
-            JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform2<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2<8, 3>::kSmem));
-            JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform2<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2<8, 2>::kSmem));
-            JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform2<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2<16, 2>::kSmem));
-            JZ_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->fwd2_occ[0], k_fwd_transform2<8, 3>, Fwd2<8, 3>::kThreads, Fwd2<8, 3>::kSmem));
-            JZ_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->fwd2_occ[1], k_fwd_transform2<8, 2>, Fwd2<8, 2>::kThreads, Fwd2<8, 2>::kSmem));
-            JZ_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->fwd2_occ[2], k_fwd_transform2<16, 2>, Fwd2<16, 2>::kThreads, Fwd2<16, 2>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform2<8, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2<8, 3>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform2<8, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2<8, 3>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaFuncSetAttribute(k_fwd_transform2<8, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2<8, 4>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->fwd2_occ[0], k_fwd_transform2<8, 3, true>, Fwd2<8, 3>::kThreads, Fwd2<8, 3>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->fwd2_occ[1], k_fwd_transform2<8, 3, false>, Fwd2<8, 3>::kThreads, Fwd2<8, 3>::kSmem));
+            JZ_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->fwd2_occ[2], k_fwd_transform2<8, 4, true>, Fwd2<8, 4>::kThreads, Fwd2<8, 4>::kSmem));
             JZ_CUDA_TRY(ctx, cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
             ctx->fwd2_attr_set = true;
         }
-        const int T = cfg / 10 == 16 ? 16 : 8, v = T == 16 ? 2 : (cfg % 10 == 2 ? 1 : 0);
+        const int T = 8, v = cfg == 82 ? 1 : (cfg == 84 ? 2 : 0);
         const uint32_t tpr = (p.HU + T - 1) / T;
         const uint64_t ntiles64 = uint64_t(tpr) * p.VU * nimg;
         if (ntiles64 > 0xffffffffull) return ctx->fail(JPEZYB200_EINVAL, "too many tiles");
@@ -353,9 +355,9 @@ static int launch_fwd_kernel(jpezyb200_ctx* ctx, const FwdParams& p, uint32_t ni
         ts.dbx = (grid % per_img) % tpr;
         static const uint32_t tsflags = [] { const char* e = std::getenv("JPEZY_B200_FWD_FLAGS"); return e ? uint32_t(std::atoi(e)) : 0u; }();
         ts.flags = tsflags;
-        if (v == 0) (void)jz_launch(k_fwd_transform2<8, 3>, dim3(grid), dim3(Fwd2<8, 3>::kThreads), Fwd2<8, 3>::kSmem, st, p, ntiles, ts);
-        else if (v == 1) (void)jz_launch(k_fwd_transform2<8, 2>, dim3(grid), dim3(Fwd2<8, 2>::kThreads), Fwd2<8, 2>::kSmem, st, p, ntiles, ts);
-        else (void)jz_launch(k_fwd_transform2<16, 2>, dim3(grid), dim3(Fwd2<16, 2>::kThreads), Fwd2<16, 2>::kSmem, st, p, ntiles, ts);
+        if (v == 0) (void)jz_launch(k_fwd_transform2<8, 3, true>, dim3(grid), dim3(Fwd2<8, 3>::kThreads), Fwd2<8, 3>::kSmem, st, p, ntiles, ts);
+        else if (v == 1) (void)jz_launch(k_fwd_transform2<8, 3, false>, dim3(grid), dim3(Fwd2<8, 3>::kThreads), Fwd2<8, 3>::kSmem, st, p, ntiles, ts);
+        else (void)jz_launch(k_fwd_transform2<8, 4, true>, dim3(grid), dim3(Fwd2<8, 4>::kThreads), Fwd2<8, 4>::kSmem, st, p, ntiles, ts);
     } else {
         dim3 grid((p.HU + kTileMcu - 1) / kTileMcu, p.VU, nimg);
         if (ctx->transform_variant == 2) (void)jz_launch(k_fwd_transform_t<false>, grid, dim3(256), 0, st, p);    // one thread per block (A/B runs)

@@ -147,25 +147,30 @@ __device__ __forceinline__ int dc_only_value(int c, int q)
     return __double2int_rz(__dadd_rn(__dmul_rn(term, 0.25), 128.0));
 }
 
-// slow half of one block row: truncation toward zero of every sample (the fast path floors), guard-band samples queued
-__device__ __noinline__ uint4 inv_row_slow(const float (&v)[8], float guard, uint32_t blk, int y, uint32_t* s_nfix, uint16_t* s_fix)
+// slow half of one block row: truncation toward zero of every sample (the fast path floors), guard-band samples queued.
+// (The samples travel in registers: an array argument would be built in local memory on the hot path.)
+__device__ __forceinline__ uint32_t inv_slow_sample(float v, float guard, uint32_t entry, uint32_t* s_nfix, uint16_t* s_fix)
 {
-    uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll 1
-    for (int x = 0; x < 8; ++x) {
-        const float kf = (v[x] + kMagic15) - kMagic15;
-        if (fabsf(v[x] - kf) < guard) push_fix16(s_nfix, s_fix, (blk << 7) | uint32_t(y * 8 + x));
-        const uint32_t iv = uint32_t(__float2int_rz(v[x])) & 0xffffu;
-        if (x == 0) w[0] |= iv;
-        else if (x == 1) w[0] |= iv << 16;
-        else if (x == 2) w[1] |= iv;
-        else if (x == 3) w[1] |= iv << 16;
-        else if (x == 4) w[2] |= iv;
-        else if (x == 5) w[2] |= iv << 16;
-        else if (x == 6) w[3] |= iv;
-        else w[3] |= iv << 16;
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
+    const float kf = (v + kMagic15) - kMagic15;
+    if (fabsf(v - kf) < guard) push_fix16(s_nfix, s_fix, entry);
+    return uint32_t(__float2int_rz(v)) & 0xffffu;
+}
+__device__ __noinline__ uint4 inv_row_slow(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7, float guard, uint32_t blk,
+                                           int y, uint32_t* s_nfix, uint16_t* s_fix)
+{
+    const uint32_t e = (blk << 7) | uint32_t(y * 8);
+    uint4 w;
+    w.x = inv_slow_sample(v0, guard, e, s_nfix, s_fix) | (inv_slow_sample(v1, guard, e + 1, s_nfix, s_fix) << 16);
+    w.y = inv_slow_sample(v2, guard, e + 2, s_nfix, s_fix) | (inv_slow_sample(v3, guard, e + 3, s_nfix, s_fix) << 16);
+    w.z = inv_slow_sample(v4, guard, e + 4, s_nfix, s_fix) | (inv_slow_sample(v5, guard, e + 5, s_nfix, s_fix) << 16);
+    w.w = inv_slow_sample(v6, guard, e + 6, s_nfix, s_fix) | (inv_slow_sample(v7, guard, e + 7, s_nfix, s_fix) << 16);
+    return w;
+}
+// colour_exact4 with the four luma samples in registers
+__device__ __noinline__ uint32_t colour_exact4r(int y0, int y1, int y2, int y3, uint32_t cc0, uint32_t cc1, int which)
+{
+    const int y[4] = {y0, y1, y2, y3};
+    return colour_exact4(y, sx_lo(cc0), sx_hi(cc0), sx_lo(cc1), sx_hi(cc1), which);
 }
 
 // the colour offsets of one chroma pair (phase 1c of k_inv_transform): fr | fg << 16 and fb | suspect << 16
@@ -180,6 +185,22 @@ __device__ __forceinline__ uint2 chroma_offsets(int cb, int cr)
     const bool near_int = fabsf(tg - kf) < 7.5e-5f && ((cb ^ 128) | (cr ^ 128)) != 0;
     const bool wild = (uint32_t(cb + 128) | uint32_t(cr + 128)) > 512u;
     return make_uint2(__byte_perm(uint32_t(fr), uint32_t(fg), 0x5410), (uint32_t(fb) & 0xffffu) | ((near_int || wild) ? 0x10000u : 0u));
+}
+
+// the same from the packed samples cb | cr << 16, without conversion instructions: floor(x) is the low mantissa bits of
+// x + 1.5 * 2^23 rounded down (|x| < 2^22), two of the three offsets share packed instructions
+__device__ __forceinline__ uint2 chroma_offsets_w(uint32_t ccw)
+{
+    const f32x2 ab = add2(pk2(float(sx_lo(ccw)), float(sx_hi(ccw))), pk2(-128.0f, -128.0f));       // (cb - 128, cr - 128)
+    const f32x2 fl = add2_rm(mul2(ab, pk2(1.7718f, 1.4020f)), pk2(kMagic15, kMagic15));           // floor(a * 1.7718) | floor(b * 1.4020)
+    const float a = lo2(ab), b = hi2(ab);
+    const float tg = fmaf(b, -0.7139f, a * -0.3441f);
+    float fgm;
+    asm("add.rm.f32 %0, %1, %2;" : "=f"(fgm) : "f"(tg), "f"(kMagic15));
+    const float kf = (tg + kMagic15) - kMagic15;
+    const bool near_int = fabsf(tg - kf) < 7.5e-5f && ccw != 0x00800080u;
+    const bool wild = fmaxf(fabsf(a), fabsf(b)) > 256.0f;
+    return make_uint2(__byte_perm(uint32_t(fl >> 32), __float_as_uint(fgm), 0x5410), (uint32_t(fl) & 0xffffu) | ((near_int || wild) ? 0x10000u : 0u));
 }
 
 template <int T>
@@ -289,10 +310,10 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 5 : 2) k_inv_transform2(const
 #define JZ_LOAD_COEF(V, ZW, K, MM, WW)                                                                                   \
     {                                                                                                                     \
         const uint32_t ad = add_byte<K>(ZW, base);                                                                        \
-        short ca, cb;                                                                                                     \
-        asm volatile("ld.shared.s16 %0, [%1];" : "=h"(ca) : "r"(ad));                                                     \
-        asm volatile("ld.shared.s16 %0, [%1];" : "=h"(cb) : "r"(ad + dAB));                                               \
-        const f32x2 f = pk2(float(int(ca)), float(int(cb)));                                                              \
+        int ca, cb;                            /* (32-bit destinations: I2FP instead of the quarter-rate I2F.S16) */        \
+        asm volatile("ld.shared.s16 %0, [%1];" : "=r"(ca) : "r"(ad));                                                     \
+        asm volatile("ld.shared.s16 %0, [%1];" : "=r"(cb) : "r"(ad + dAB));                                               \
+        const f32x2 f = pk2(float(ca), float(cb));                                                                        \
         d[V] = mul2(f, MM);                                                                                               \
         const f32x2 g = mul2(f, WW);                                                                                      \
         gs = add2(gs, pk2(fabsf(lo2(g)), fabsf(hi2(g))));                                                                 \
@@ -362,20 +383,14 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 5 : 2) k_inv_transform2(const
                 rowA = make_uint4(va * 0x10001u, va * 0x10001u, va * 0x10001u, va * 0x10001u);
                 exact += 8;
             } else if ((ma < lo2(gs) || negA) && valid) {
-                float v[8];
-#pragma unroll
-                for (int x = 0; x < 8; ++x) v[x] = lo2(d[x]);
-                rowA = inv_row_slow(v, lo2(gs), blkA, int(sub), s_nfix, s_fix);
+                rowA = inv_row_slow(lo2(d[0]), lo2(d[1]), lo2(d[2]), lo2(d[3]), lo2(d[4]), lo2(d[5]), lo2(d[6]), lo2(d[7]), lo2(gs), blkA, int(sub), s_nfix, s_fix);
             }
             if (dcoB) {
                 const uint32_t vb = uint32_t(dc_only_value(dcB, qB)) & 0xffffu;
                 rowB = make_uint4(vb * 0x10001u, vb * 0x10001u, vb * 0x10001u, vb * 0x10001u);
                 exact += 8;
             } else if ((mb < hi2(gs) || negB) && valid) {
-                float v[8];
-#pragma unroll
-                for (int x = 0; x < 8; ++x) v[x] = hi2(d[x]);
-                rowB = inv_row_slow(v, hi2(gs), blkB, int(sub), s_nfix, s_fix);
+                rowB = inv_row_slow(hi2(d[0]), hi2(d[1]), hi2(d[2]), hi2(d[3]), hi2(d[4]), hi2(d[5]), hi2(d[6]), hi2(d[7]), hi2(gs), blkB, int(sub), s_nfix, s_fix);
             }
             exact = __reduce_add_sync(0xffffffffu, valid ? exact : 0u);
             if (lane == 0 && exact) atomicAdd(p.guard_counter, (unsigned long long)exact);
@@ -386,18 +401,12 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 5 : 2) k_inv_transform2(const
             *reinterpret_cast<uint4*>(dst) = rowA;
             *reinterpret_cast<uint4*>(dst + 8 * C::kYRow) = rowB;
         } else {
+            // the (Cb, Cr) samples, interleaved; the colour offsets are derived from them by the threads of the colour phase
+            // (the chroma lanes would otherwise keep the luma warps waiting at the barrier)
             const uint32_t cbw[4] = {rowA.x, rowA.y, rowA.z, rowA.w}, crw[4] = {rowB.x, rowB.y, rowB.z, rowB.w};
-            uint2 off[8];
             uint32_t cc[8];
 #pragma unroll
-            for (int x = 0; x < 8; ++x) {
-                const int cb = (x & 1) ? sx_hi(cbw[x >> 1]) : sx_lo(cbw[x >> 1]), cr = (x & 1) ? sx_hi(crw[x >> 1]) : sx_lo(crw[x >> 1]);
-                off[x] = chroma_offsets(cb, cr);
-                cc[x] = (uint32_t(cb) & 0xffffu) | (uint32_t(cr) << 16);
-            }
-            uint4* od = reinterpret_cast<uint4*>(s_off + sub * C::kOffRow + mcu * 64u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) od[k] = make_uint4(off[2 * k].x, off[2 * k].y, off[2 * k + 1].x, off[2 * k + 1].y);
+            for (int k = 0; k < 4; ++k) cc[2 * k] = __byte_perm(cbw[k], crw[k], 0x5410), cc[2 * k + 1] = __byte_perm(cbw[k], crw[k], 0x7632);
             uint4* cd = reinterpret_cast<uint4*>(s_cc + sub * C::kCcRow + mcu * 32u);
             cd[0] = make_uint4(cc[0], cc[1], cc[2], cc[3]), cd[1] = make_uint4(cc[4], cc[5], cc[6], cc[7]);
         }
@@ -444,23 +453,6 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 5 : 2) k_inv_transform2(const
             exact_hits = __reduce_add_sync(0xffffffffu, exact_hits);
             if (lane == 0 && exact_hits) atomicAdd(p.guard_counter, (unsigned long long)exact_hits);
             __syncthreads();
-            // the offsets of the chroma pairs whose samples were (possibly) replaced
-            if (!p.gray) {
-                const uint32_t npair = overflow ? nvalid * 64u : nfix;
-                for (uint32_t i = t; i < npair; i += C::kThreads) {
-                    uint32_t m, y, x;
-                    if (overflow) m = i >> 6, y = (i >> 3) & 7u, x = i & 7u;
-                    else {
-                        const uint32_t e = s_fix[i], blk = e >> 7;
-                        m = blk / 6u;
-                        if (blk - m * 6u < 4u) continue;
-                        y = (e >> 3) & 7u, x = e & 7u;
-                    }
-                    const uint32_t ccw = *reinterpret_cast<const uint32_t*>(s_cc + y * C::kCcRow + (m * 8u + x) * 4u);
-                    *reinterpret_cast<uint2*>(s_off + y * C::kOffRow + (m * 8u + x) * 8u) = chroma_offsets(sx_lo(ccw), sx_hi(ccw));
-                }
-            }
-            __syncthreads();
         }
     }
 
@@ -471,6 +463,16 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 5 : 2) k_inv_transform2(const
     if (t < T * 16) {
         const uint32_t ry = uint32_t(t) / T, m = uint32_t(t) % T;
         const uint32_t x0 = (mx0 + m) * 16u;
+        if (!p.gray) {
+            // colour offsets of chroma row ry / 2: this thread derives pairs 0..3 (even ry) or 4..7 (odd ry), the thread of the other
+            // row of the pair -- T lanes away, same warp -- the other four
+            const uint32_t h4 = (ry & 1u) * 4u;
+            const uint4 ccq = *reinterpret_cast<const uint4*>(s_cc + (ry >> 1) * C::kCcRow + (m * 8u + h4) * 4u);
+            const uint2 f0 = chroma_offsets_w(ccq.x), f1 = chroma_offsets_w(ccq.y), f2 = chroma_offsets_w(ccq.z), f3 = chroma_offsets_w(ccq.w);
+            uint4* od = reinterpret_cast<uint4*>(s_off + (ry >> 1) * C::kOffRow + (m * 8u + h4) * 8u);
+            od[0] = make_uint4(f0.x, f0.y, f1.x, f1.y), od[1] = make_uint4(f2.x, f2.y, f3.x, f3.y);
+            __syncwarp();
+        }
         if (m < nvalid) {
             const uint4 ya = *reinterpret_cast<const uint4*>(s_y + ry * C::kYRow + m * 32u);
             const uint4 yb = *reinterpret_cast<const uint4*>(s_y + ry * C::kYRow + m * 32u + 16u);
@@ -491,12 +493,11 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 5 : 2) k_inv_transform2(const
                     const int y0 = sx_lo(yw[c0]), y1 = sx_hi(yw[c0]), y2 = sx_lo(yw[c1]), y3 = sx_hi(yw[c1]);
                     if ((ob[c0] | ob[c1]) & 0x10000u) {
                         // rare: the reference's FP64 expressions, from the stored chroma samples
-                        const int yi[4] = {y0, y1, y2, y3};
                         const uint32_t* pcc = reinterpret_cast<const uint32_t*>(s_cc + (ry >> 1) * C::kCcRow + (m * 8u + c0) * 4u);
                         const uint32_t w0 = pcc[0], w1 = pcc[1];
-                        ro[q4] = colour_exact4(yi, sx_lo(w0), sx_hi(w0), sx_lo(w1), sx_hi(w1), 0);
-                        go[q4] = colour_exact4(yi, sx_lo(w0), sx_hi(w0), sx_lo(w1), sx_hi(w1), 1);
-                        bo[q4] = colour_exact4(yi, sx_lo(w0), sx_hi(w0), sx_lo(w1), sx_hi(w1), 2);
+                        ro[q4] = colour_exact4r(y0, y1, y2, y3, w0, w1, 0);
+                        go[q4] = colour_exact4r(y0, y1, y2, y3, w0, w1, 1);
+                        bo[q4] = colour_exact4r(y0, y1, y2, y3, w0, w1, 2);
                     } else {
                         const int fr0 = sx_lo(oa[c0]), fg0 = sx_hi(oa[c0]), fb0 = sx_lo(ob[c0]);
                         const int fr1 = sx_lo(oa[c1]), fg1 = sx_hi(oa[c1]), fb1 = sx_lo(ob[c1]);
@@ -512,12 +513,13 @@ __global__ void __launch_bounds__(T * 24, T == 8 ? 5 : 2) k_inv_transform2(const
                 *reinterpret_cast<uint4*>(G + rowoff + x0) = make_uint4(go[0], go[1], go[2], go[3]);
                 *reinterpret_cast<uint4*>(B + rowoff + x0) = make_uint4(bo[0], bo[1], bo[2], bo[3]);
             } else {
-#pragma unroll 1
+#pragma unroll           // (fully unrolled: a run-time index would send the three arrays to local memory)
                 for (int i = 0; i < 16; ++i) {
-                    if (x0 + i >= p.W) break;
-                    R[rowoff + x0 + i] = uint8_t(ro[i >> 2] >> (8 * (i & 3)));
-                    G[rowoff + x0 + i] = uint8_t(go[i >> 2] >> (8 * (i & 3)));
-                    B[rowoff + x0 + i] = uint8_t(bo[i >> 2] >> (8 * (i & 3)));
+                    if (x0 + i < p.W) {
+                        R[rowoff + x0 + i] = uint8_t(ro[i >> 2] >> (8 * (i & 3)));
+                        G[rowoff + x0 + i] = uint8_t(go[i >> 2] >> (8 * (i & 3)));
+                        B[rowoff + x0 + i] = uint8_t(bo[i >> 2] >> (8 * (i & 3)));
+                    }
                 }
             }
         }

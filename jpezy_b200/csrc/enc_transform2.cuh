@@ -85,8 +85,9 @@ __device__ __forceinline__ float fmax3_abs(float a, float b, float c)
 // ---- constants of the second-generation kernel --------------------------------------------------------------------
 // per (class, column j) the eight multipliers of coefficients (0..7, j) as (K, K) pairs, the guard bands, the zig-zag positions
 struct Q2Tab {
-    float2 K[2][8][8];     // [class][j][i]: (K, K) of coefficient (i, j); K of the DC coefficient carries the factor 1 - 2^-20
-    float G[2][8][8];      // [class][j][i]: guard band in w units
+    float2 K[2][4][8][2];  // [class][i / 2][j][i % 2]: (K, K) of coefficient (i, j); K of the DC coefficient carries the factor 1 - 2^-20.
+                           // The eight column lanes j of a pair read 16 bytes each, 128 contiguous bytes: no bank conflicts
+    float G[2][8][8];      // [class][i][j]: guard band in w units (the lanes j read eight neighbouring words)
     uint2 izz[8];          // [j]: zig-zag positions of coefficients (0..7, j), one byte each
     uint32_t thr[2];       // bit pattern of 1 - 2 Gmax: |w| below it quantises to 0 whatever the coefficient
     uint32_t pad[2];
@@ -293,7 +294,7 @@ struct Fwd2 {
 // How the tile ids advance from one tile of a CTA to its next (id += gridDim.x), precomputed on the host: no divisions in the loop
 struct TileStep {
     uint32_t tiles_per_row, dimg, dmy, dbx;
-    uint32_t flags;      // experiments: bit 0 = the DMA warp issues a tile's bulk copies from one lane instead of 32
+    uint32_t flags;      // experiments: bit 0 = the DMA warp issues a tile's bulk copies from one lane instead of 32; bit 1 = fixed warp roles
 };
 
 // Persistent, warp-specialised CTAs.  CTA b transforms tiles b, b + gridDim.x, ... (a tile = T MCUs of one MCU row of one image).
@@ -301,7 +302,10 @@ struct TileStep {
 //    barriers) and sends every finished tile's coefficients off with one bulk store (`out_full` / `out_empty`);
 //  * the compute warps never meet at a CTA barrier: a warp owns its four block pairs from the pixels to the coefficients and to its
 //    own fix-up queue; it tells the DMA warp through `in_empty` / `out_full` when it is done with a stage / a staging buffer.
-template <int T, int NST>
+// WST (warp stores): every compute warp sends its own eight blocks off (its own two staging areas, its own bulk-store groups)
+// instead of handing the tile to the DMA warp: no warp ever waits for the slowest warp of the tile on the output side, only for
+// its own store of two tiles ago.
+template <int T, int NST, bool WST>
 __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(const FwdParams p, const uint32_t ntiles, const TileStep ts)
 {
     using C = Fwd2<T, NST>;
@@ -381,17 +385,21 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
                 issue(lst);
                 lst = lst + 1 == NST ? 0 : lst + 1;
             }
-            if (lane == 0) {
-                const uint32_t ob = i & 1u;
-                mbar_wait_wd(bar_out_full + 8u * ob, (i >> 1) & 1u);
-                const uint32_t mx0 = bx * T, nvalid = min(uint32_t(T), p.HU - mx0);
-                bulk_s2g(p.coefs + size_t(img) * p.coef_stride + (size_t(my) * p.HU + mx0) * 384, sm + C::oOut + ob * C::kOut, nvalid * 768u);
-                bulk_commit();
-                bulk_wait_read0();                           // the store has read the staging buffer (not: has reached memory)
-                mbar_arrive(bar_out_empty + 8u * ob);
+            if constexpr (WST) {
+                if (lid >= ntiles) break;                        // nothing left to load: the compute warps store their tiles themselves
+            } else {
+                if (lane == 0) {
+                    const uint32_t ob = i & 1u;
+                    mbar_wait_wd(bar_out_full + 8u * ob, (i >> 1) & 1u);
+                    const uint32_t mx0 = bx * T, nvalid = min(uint32_t(T), p.HU - mx0);
+                    bulk_s2g(p.coefs + size_t(img) * p.coef_stride + (size_t(my) * p.HU + mx0) * 384, sm + C::oOut + ob * C::kOut, nvalid * 768u);
+                    bulk_commit();
+                    bulk_wait_read0();                           // the store has read the staging buffer (not: has reached memory)
+                    mbar_arrive(bar_out_empty + 8u * ob);
+                }
+                __syncwarp();
+                advance(img, my, bx);
             }
-            __syncwarp();
-            advance(img, my, bx);
         }
         return;
     }
@@ -400,16 +408,16 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
     // the quantisation constants come to shared memory while the first tile is in flight (a barrier of the compute warps only)
     for (uint32_t i = t; i < sizeof(Q2Tab) / 4; i += C::kWarps * 32) sts32(sm + C::oTab + 4u * i, reinterpret_cast<const uint32_t*>(&gQ2)[i]);
     asm volatile("bar.sync 1, %0;" ::"r"(C::kWarps * 32) : "memory");
-    const uint32_t pr = uint32_t(t) >> 3, sub = uint32_t(t) & 7u;    // block pair, row (phase 1) / column (phase 2)
-    const bool luma = pr < 2u * T;                                   // warp uniform (4 pairs per warp)
-    const uint32_t mcu = luma ? (pr >> 1) : pr - 2u * T;
-    const uint32_t blkA = luma ? mcu * 6u + (pr & 1u) : mcu * 6u + 4u;
-    const uint32_t dAB = luma ? 256u : 128u;                         // block B = Y2 / Y3 / Cr: bytes behind block A
-    const uint32_t a_mid = sm + C::oMid + pr * C::kPair;
-    const bool work = luma || !p.gray;                               // --gray: Cb = Cr = 0 (:61-64), the chroma blocks are all zero
+    const uint32_t sub = uint32_t(t) & 7u;                           // row (phase 1) / column (phase 2) of the lane's block pair
+    const uint32_t a_mid = sm + C::oMid + (uint32_t(t) >> 3) * C::kPair;
     const uint32_t a_fix = sm + C::oFix + warp * (kWarpFix * 2), a_cnt = sm + C::oCnt + 4u * warp;
     const uint32_t a_tab = sm + C::oTab;
-    const int cls = luma ? 0 : 1;
+    // Which four block pairs of the tile a warp takes changes from tile to tile: two thirds of the roles are luma pairs, one third
+    // chroma pairs, and a chroma tile costs a warp more than a luma tile (FP64 colour conversion).  With fixed roles the luma warps
+    // would wait for the chroma warps at every staging buffer (13 % of the warp samples of the first version); with six warps the
+    // role advances by two per tile, so every warp sees luma, luma, chroma, ... and exactly two warps hold chroma roles at any tile.
+    const uint32_t rot = (C::kWarps == 6 && !(ts.flags & 2u)) ? 2u : 0u;
+    uint32_t role = uint32_t(warp);
     uint32_t sgn_bit, m23_bits;          // kept out of the immediate fields (trunc_div2)
     asm volatile("mov.u32 %0, 0x80000000;" : "=r"(sgn_bit));
     asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(m23_bits));
@@ -418,12 +426,28 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
 #pragma unroll 1
     for (uint32_t id = blockIdx.x; id < ntiles; id += gridDim.x, ++i) {
         const uint32_t ob = i & 1u;
+        const uint32_t pr = role * 4u + (uint32_t(lane) >> 3);            // block pair of this lane in this tile
+        const bool luma = pr < 2u * T;                                   // warp uniform (4 pairs per warp)
+        const uint32_t mcu = luma ? (pr >> 1) : pr - 2u * T;
+        const uint32_t blkA = luma ? mcu * 6u + (pr & 1u) : mcu * 6u + 4u;
+        const uint32_t dAB = luma ? 256u : 128u;                         // block B = Y2 / Y3 / Cr: bytes behind block A
+        const bool work = luma || !p.gray;                               // --gray: Cb = Cr = 0 (:61-64), the chroma blocks are all zero
+        const uint32_t cls = luma ? 0u : 1u;
         const uint32_t mx0 = bx * T, nvalid = min(uint32_t(T), p.HU - mx0);
         const int hlast = int(min(15u, p.H - 1u - (p.row0 + my) * 16u));   // last staged row; rows below replicate it (:101)
         const bool valid = mcu < nvalid;
         const uint32_t a_in = sm + C::oIn + st * C::kIn;
-        const uint32_t a_outA = sm + C::oOut + ob * C::kOut + blkA * 128u;
-        if (i >= 2) mbar_wait_wd(bar_out_empty + 8u * ob, ((i >> 1) - 1u) & 1u);    // the store of tile i - 2 has read this buffer
+        // staging: WST -- the warp's own area, its blocks in the order they have in the coefficient array ([Y0 Y1 Y2 Y3] of its two
+        // MCUs, [Cb Cr] of its four); otherwise the tile's area, shared by the warps
+        const uint32_t a_wst = sm + C::oOut + uint32_t(warp) * 2048u + ob * 1024u;
+        const uint32_t pl = uint32_t(lane) >> 3;
+        const uint32_t a_outA = WST ? a_wst + (luma ? (pl >> 1) * 512u + (pl & 1u) * 128u : pl * 256u) : sm + C::oOut + ob * C::kOut + blkA * 128u;
+        if constexpr (WST) {
+            if (i >= 2 && lane == 0) bulk_wait_read1();      // this warp's stores of tile i - 2 have read the area
+            __syncwarp();
+        } else {
+            if (i >= 2) mbar_wait_wd(bar_out_empty + 8u * ob, ((i >> 1) - 1u) & 1u);    // the store of tile i - 2 has read this buffer
+        }
         // this lane's share of the pair's staging area starts as zeros: only non-zero coefficients are stored
         sts128(a_outA + sub * 16u, 0, 0, 0, 0);
         sts128(a_outA + dAB + sub * 16u, 0, 0, 0, 0);
@@ -502,10 +526,10 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
 #pragma unroll
                 for (int k = 0; k < 8; ++k) d[k] = lds64x(a_mid + k * C::kPairRow + j * 8u);
                 aan_fdct8_x2(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]);
-                const uint32_t kq = a_tab + uint32_t(offsetof(Q2Tab, K)) + (cls * 8u + j) * 64u;
+                const uint32_t kq = a_tab + uint32_t(offsetof(Q2Tab, K)) + cls * 512u + j * 16u;
 #pragma unroll
                 for (int k = 0; k < 8; k += 2) {
-                    const uint4 kk = lds128(kq + 8 * k);
+                    const uint4 kk = lds128(kq + 64 * k);
                     w[k] = mul2(d[k], (unsigned long long)kk.x | ((unsigned long long)kk.y << 32));
                     w[k + 1] = mul2(d[k + 1], (unsigned long long)kk.z | ((unsigned long long)kk.w << 32));
                 }
@@ -519,7 +543,7 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
             // five high rows (rarely alive in photographic content) share a first test.
             const uint32_t thr = lds32(a_tab + uint32_t(offsetof(Q2Tab, thr)) + 4u * cls);
             const uint2 izz = lds64(a_tab + uint32_t(offsetof(Q2Tab, izz)) + 8u * j);
-            const uint32_t a_g = a_tab + uint32_t(offsetof(Q2Tab, G)) + (cls * 8u + j) * 32u;
+            const uint32_t a_g = a_tab + uint32_t(offsetof(Q2Tab, G)) + cls * 256u + j * 4u;
             float am[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) am[k] = fmaxf(fabsf(lo2(w[k])), fabsf(hi2(w[k])));
@@ -531,7 +555,7 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
                 if (k >= 3 && !any_hi) break;
                 if (__reduce_max_sync(0xffffffffu, valid ? __float_as_uint(am[k]) : 0u) < thr) continue;
                 const uint32_t zz = __byte_perm(k < 4 ? izz.x : izz.y, 0, 0x4440 + (k & 3));
-                const float g = __uint_as_float(lds32(a_g + 4u * k));
+                const float g = __uint_as_float(lds32(a_g + 32u * k));
                 const f32x2 mg = pk2(kMagic15, kMagic15);
                 const f32x2 dl = sub2(w[k], sub2(add2(w[k], mg), mg));          // w - rint(w)
                 const uint32_t a_o = a_outA + 2u * zz, gbit = 1u << (zz >> 3);
@@ -555,7 +579,7 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
                 const bool overflow = nfix > uint32_t(kWarpFix);
                 // overflow (adversarial content): every AC coefficient of the warp's eight blocks
                 const uint32_t nent = overflow ? 8u * 63u : nfix;
-                const uint32_t wblk0 = luma ? uint32_t(warp) * 12u : (uint32_t(warp) - 2u * T / 4u) * 24u + 4u;      // first block of the warp's pairs
+                const uint32_t wblk0 = luma ? role * 12u : (role - 2u * T / 4u) * 24u + 4u;      // first block of the warp's pairs
                 for (uint32_t e0 = 0; e0 < nent; e0 += 4) {
                     const uint32_t e = e0 + (uint32_t(lane) >> 3);
                     bool actv = e < nent;
@@ -581,7 +605,12 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
                         const int q = cC.quant[(blk % 6u) >= 4u][ij];
                         const int v = requant_finish_s<C::kRow>(part, a_in, blk, int(ci), int(cj), q, hlast, p.gray, p.guard_counter);
                         const uint32_t zz = cC.izz[ij];
-                        sts16(sm + C::oOut + ob * C::kOut + blk * 128u + 2u * zz, v);
+                        uint32_t a_b = sm + C::oOut + ob * C::kOut + blk * 128u;
+                        if constexpr (WST) {
+                            const uint32_t bm = blk / 6u, bk = blk - bm * 6u;        // the warp's own blocks only
+                            a_b = a_wst + (luma ? (bm - role * 2u) * 512u + bk * 128u : (bm - (role - 2u * T / 4u) * 4u) * 256u + (bk - 4u) * 128u);
+                        }
+                        sts16(a_b + 2u * zz, v);
                     }
                 }
                 __syncwarp();
@@ -610,11 +639,31 @@ __global__ void __launch_bounds__(T * 24 + 32, T == 8 ? 4 : 2) k_fwd_transform2(
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive(bar_out_full + 8u * ob);
+            if constexpr (WST) {
+                int16_t* dst = p.coefs + size_t(img) * p.coef_stride + (size_t(my) * p.HU + mx0) * 384;
+                if (luma) {
+#pragma unroll
+                    for (uint32_t m = 0; m < 2; ++m)
+                        if (role * 2u + m < nvalid) bulk_s2g(dst + (role * 2u + m) * 384u, a_wst + m * 512u, 512u);
+                } else {
+                    const uint32_t m0 = (role - 2u * T / 4u) * 4u;
+#pragma unroll
+                    for (uint32_t m = 0; m < 4; ++m)
+                        if (m0 + m < nvalid) bulk_s2g(dst + (m0 + m) * 384u + 256u, a_wst + m * 256u, 256u);
+                }
+                bulk_commit();
+            } else {
+                mbar_arrive(bar_out_full + 8u * ob);
+            }
             mbar_arrive(bar_in_empty + 8u * st);
         }
         if (++st == NST) st = 0, stpar ^= 1u;
+        role += rot;
+        if (role >= uint32_t(C::kWarps)) role -= uint32_t(C::kWarps);
         advance(img, my, bx);
+    }
+    if constexpr (WST) {
+        if (lane == 0) bulk_wait_read0();        // shared memory must outlive the reads of the last stores
     }
 }
 

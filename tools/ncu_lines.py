@@ -1,5 +1,5 @@
 """Executed warp instructions and stall samples per source line of an ncu report captured with --import-source on.
-usage: python tools/ncu_lines.py report.ncu-rep [npixels] [top]     (source text is read from the working tree)"""
+usage: python tools/ncu_lines.py report.ncu-rep [npixels] [top] [kernel regex]     (source text is read from the working tree)"""
 import collections
 import csv
 import os
@@ -13,7 +13,10 @@ def main():
     rep = sys.argv[1]
     npx = float(sys.argv[2]) if len(sys.argv) > 2 else 3840 * 2160
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]
+    if len(sys.argv) > 4:
+        cmd += ["-k", "regex:" + sys.argv[4]]
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     cur, hdr = None, None
     per = collections.defaultdict(lambda: [0, 0, 0])
     for r in csv.reader(out.splitlines()):

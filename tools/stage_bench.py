@@ -22,12 +22,15 @@ def main():
     ap.add_argument("--gray", action="store_true")
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--variant", type=int, default=0, help="JPEZYB200_OPT_TRANSFORM")
+    ap.add_argument("--lib", default="", help="A/B runs: another build of libjpezy_b200.so to load instead of the in-tree one")
     a = ap.parse_args()
     import numpy as np
     import torch
     import jpezy_b200 as J
     from jpezy_b200 import capi
 
+    if a.lib:
+        capi.library_path = lambda: os.path.abspath(a.lib)
     ctx = J.Context(0)
     if a.variant:
         ctx.set_option(capi.OPT_TRANSFORM, a.variant)
@@ -77,7 +80,7 @@ def main():
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
-    print(json.dumps({"stage": a.stage, "W": W, "H": H, "batch": B, "family": a.family, "gray": gray, "variant": a.variant,
+    print(json.dumps({"stage": a.stage, "W": W, "H": H, "batch": B, "family": a.family, "gray": gray, "variant": a.variant, "lib": os.path.basename(a.lib),
                       "tile": os.environ.get("JPEZY_B200_FWD_TILE", ""), "us_per_launch": round(us, 2), "GBs": round(gbs, 1),
                       "frac_of_measured_peak": round(gbs / peak, 4), "guard_fwd": ctx.stat(capi.STAT_GUARD_FWD),
                       "sync_iters": [ctx.stat(capi.STAT_SYNC_ITERS0), ctx.stat(capi.STAT_SYNC_ITERS1)], "sync_rounds": ctx.stat(capi.STAT_SYNC_ROUNDS)}))
