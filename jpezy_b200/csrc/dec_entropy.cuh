@@ -64,6 +64,9 @@ static_assert(sizeof(HuffSlow) % 4 == 0 && sizeof(HuffDecTab) % 16 == 0, "copied
 struct DecTabs {
     uint32_t fast[4][1 << kLutBits];
     HuffSlow slow[4];
+    // per block b of the MCU (decode_span): x = shared address of the AC table of block b; y = shared address of the DC table of the
+    // block after b (low 24 bits) | index of that block << 24
+    uint2 binfo[16];
 };
 
 struct DecParams {
@@ -216,40 +219,95 @@ struct FastBits {
 // Decode from (br.pos, b, z) until br.pos >= end (or >= limit); positions are relative to the span.  With kWrite the
 // coefficients that carry a value field are stored (the buffer is pre-zeroed), block ordinals start at blk.
 // Tables: T->fast[0] = DC class 0 (luma), [1] = DC class 1, [2] = AC class 0, [3] = AC class 1 (contiguous).
+//
+// One thread decodes one symbol after the other (ncu: ~110 cycles per symbol in the first version, the serial chain of the
+// synchronisation passes).  What sets the rate is the dependency chain  table word -> shift count -> bit window -> table address
+// -> table word,  every branch that must resolve before the next instruction may issue, and the instructions per symbol (one
+// warp per scheduler issues them in order).  So:
+//  * the symbol is consumed speculatively, as a plain symbol, into temporaries, and the table load of the NEXT symbol is issued
+//    before anything is tested; "not a plain symbol" (code longer than kLutBits, folded end-of-block that does not apply) and "end
+//    of the span" are tested while that load is in flight; the first commits nothing, corrects the entry and starts over;
+//  * both candidate windows (word boundary crossed or not) are shifted in parallel and one select picks, instead of selecting
+//    the words first; the table of the next symbol (AC of this block / DC of the next) is chosen from the zig-zag position
+//    while the window is being computed, so one load suffices and its result is the next entry without a select;
+//  * block bookkeeping (next block, its tables) comes from an 8-byte record per block position in shared memory.
 template <bool kWrite>
 __device__ __forceinline__ void decode_span(FastBits& br, uint32_t& b, uint32_t& z, uint32_t& nblocks, const uint32_t end,
                                             const uint32_t limit, const DecTabs* __restrict__ T, int16_t* __restrict__ out,
                                             int16_t* __restrict__ dcd, uint64_t blk, const uint64_t nblk, int* corrupt,
                                             const uint32_t nb, const uint32_t ny)
 {
+    (void)nb, (void)ny;
     const uint32_t stop = end < limit ? end : limit;
-    uint32_t tab;              // (opaque to the compiler, which would otherwise re-derive the shared-window address per symbol)
+    if (!(br.pos < stop)) return;
+    uint32_t tab, binfo;       // (opaque to the compiler, which would otherwise re-derive the shared-window addresses per symbol)
     asm volatile("mov.u32 %0, %1;" : "=r"(tab) : "r"(uint32_t(__cvta_generic_to_shared(&T->fast[0][0]))));
-    uint32_t bn = (b + 1u == nb) ? 0u : b + 1u;                       // the block after this one
-    uint32_t t_cont = (2u + (b >= ny ? 1u : 0u)) << kLutBits;         // AC table of this block
-    uint32_t t_new = (bn >= ny ? 1u : 0u) << kLutBits;                // DC table of the next block
-    uint32_t e = lds32(tab + (((z == 0u ? t_cont - (2u << kLutBits) : t_cont) + (br.pk >> (32 - kLutBits))) << 2));
-    while (br.pos < stop) {
-        uint32_t dz = __byte_perm(e, 0, 0x4441);
-        if (z + dz >= 128u) {      // not a plain symbol
+    asm volatile("mov.u32 %0, %1;" : "=r"(binfo) : "r"(uint32_t(__cvta_generic_to_shared(&T->binfo[0]))));
+    constexpr uint32_t kTab = 4u << kLutBits;                          // bytes per table
+    uint32_t w0 = br.hi, w1 = br.lo, w2 = br.nx, wa = br.wa, acc = br.acc, pk = br.pk, pos = br.pos;
+    uint32_t t_cont, t_new, bn;
+    {
+        uint2 bi;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bi.x), "=r"(bi.y) : "r"(binfo + 8u * b));
+        t_cont = bi.x, t_new = bi.y & 0xffffffu, bn = bi.y >> 24;
+    }
+    uint32_t e = lds32((z == 0u ? t_cont - 2u * kTab : t_cont) + ((pk >> (32 - kLutBits)) << 2));
+    for (;;) {
+        const uint32_t dz = __byte_perm(e, 0, 0x4441);
+        const uint32_t zs = z + dz;
+        // speculative consume (into temporaries) and the load of the next entry
+        const uint32_t a2 = acc + e;
+        const bool endb = zs >= 64u;
+        const uint32_t tsel = endb ? t_new : t_cont;
+        // (spelled out: left to itself the compiler predicates the second shift on the crossing test and puts three more
+        // instructions on the chain)
+        uint32_t pk2, en, crossw;
+        asm volatile(
+            "{\n\t.reg .pred c;\n\t.reg .b32 x, pa, pb, i, ad;\n\t"
+            "xor.b32 x, %3, %4;\n\t"
+            "and.b32 %2, x, 32;\n\t"
+            "setp.ne.u32 c, %2, 0;\n\t"
+            "shf.l.wrap.b32 pa, %6, %5, %3;\n\t"
+            "shf.l.wrap.b32 pb, %7, %6, %3;\n\t"
+            "selp.b32 %0, pb, pa, c;\n\t"
+            "shr.u32 i, %0, 22;\n\t"
+            "mad.lo.u32 ad, i, 4, %8;\n\t"
+            "ld.shared.u32 %1, [ad];\n\t}"
+            : "=r"(pk2), "=r"(en), "=r"(crossw)
+            : "r"(a2), "r"(acc), "r"(w0), "r"(w1), "r"(w2), "r"(tsel)
+            : "memory");
+        static_assert(kLutBits == 10, "the shift count above");
+        const bool cross = crossw != 0u;
+        uint32_t w3 = w2;
+        if (cross) w3 = lds32(wa);
+        if (zs >= 128u) {          // not a plain symbol (nothing has been committed yet)
+            const uint32_t t_cur = z == 0u ? t_cont - 2u * kTab : t_cont;
             if (dz == 255u) {      // code longer than kLutBits, or none
-                const uint32_t t_cur = z == 0u ? t_cont - (2u << kLutBits) : t_cont;
-                e = huff_lookup_slow(T->slow + (t_cur >> kLutBits), br.pk);
-                if (e == 0u) {     // no such code: only legal while speculating
+                e = huff_lookup_slow(T->slow + ((t_cur - tab) / kTab), pk);
+                if (e == 0u) {     // no such code: only legal while speculating.  One bit is dropped, the state stays
                     if (kWrite && corrupt) *corrupt = 1;
-                    br.consume(1);
-                    e = lds32(tab + ((t_cur + (br.pk >> (32 - kLutBits))) << 2));
-                    continue;
+                    const uint32_t a1 = acc + 1u;
+                    if ((a1 ^ acc) & 32u) {
+                        w0 = w1, w1 = w2, w2 = lds32(wa);
+                        wa += 4u;
+                    }
+                    acc = a1;
+                    pk = __funnelshift_l(w1, w0, a1);
+                    pos += 1u;
+                    e = lds32(t_cur + ((pk >> (32 - kLutBits)) << 2));
+                    if (pos >= stop) break;
                 }
             } else {               // the symbol fills the block itself: the bits that look like EOB are the next block's
                 e = unfold_entry(e);
             }
-            dz = __byte_perm(e, 0, 0x4441);
+            continue;
         }
-        const uint32_t w = br.pk;
-        br.consume(e);
-        const uint32_t idx = br.pk >> (32 - kLutBits);
-        const uint32_t ea = lds32(tab + ((t_cont + idx) << 2)), eb = lds32(tab + ((t_new + idx) << 2));
+        // commit
+        const uint32_t w = pk;
+        w0 = cross ? w1 : w0, w1 = cross ? w2 : w1, w2 = w3;
+        wa += crossw >> 3;
+        acc = a2, pk = pk2;
+        pos += e & 31u;
         if (kWrite) {
             const uint32_t len = (e >> 16) & 31u, sz = (e >> 21) & 15u;
             const uint32_t k = z + ((dz - 1u) & 63u);          // zig-zag index of this coefficient
@@ -263,21 +321,29 @@ __device__ __forceinline__ void decode_span(FastBits& br, uint32_t& b, uint32_t&
                 else out[blk * 64 + k] = int16_t(v);
             }
         }
-        const bool endb = z + dz >= 64u;
-        z = endb ? 0u : z + dz;
-        e = endb ? eb : ea;
+        z = endb ? 0u : zs;
         b = endb ? bn : b;
         nblocks += endb ? 1u : 0u;
         blk += endb ? 1u : 0u;
-        if (kWrite && blk >= nblk) return;
-        bn = (b + 1u == nb) ? 0u : b + 1u;
-        t_cont = (2u + (b >= ny ? 1u : 0u)) << kLutBits;
-        t_new = (bn >= ny ? 1u : 0u) << kLutBits;
+        e = en;
+        if (kWrite && blk >= nblk) break;
+        {
+            uint2 bi;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bi.x), "=r"(bi.y) : "r"(binfo + 8u * b));
+            t_cont = bi.x, t_new = bi.y & 0xffffffu, bn = bi.y >> 24;
+        }
+        if (pos >= stop) break;
     }
+    br.hi = w0, br.lo = w1, br.nx = w2, br.wa = wa, br.acc = acc, br.pk = pk, br.pos = pos;
 }
 
-__device__ __forceinline__ void load_dec_tabs(const HuffDecTab* __restrict__ tabs, DecTabs* __restrict__ T)
+__device__ __forceinline__ void load_dec_tabs(const HuffDecTab* __restrict__ tabs, DecTabs* __restrict__ T, uint32_t nb, uint32_t ny)
 {
+    if (threadIdx.x < 16) {
+        const uint32_t b = threadIdx.x, bn = b + 1u >= nb ? 0u : b + 1u;
+        const uint32_t base = uint32_t(__cvta_generic_to_shared(&T->fast[0][0]));
+        T->binfo[b] = make_uint2(base + (2u + (b >= ny ? 1u : 0u)) * (4u << kLutBits), (base + (bn >= ny ? 1u : 0u) * (4u << kLutBits)) | (bn << 24));
+    }
     constexpr int kFast16 = (1 << kLutBits) * 4 / 16, kSlowW = int(sizeof(HuffSlow) / 4);
     // eight loads in flight per thread: the tables come out of L2 at its latency, not at eight times that
     for (int i0 = threadIdx.x; i0 < 4 * kFast16; i0 += 8 * blockDim.x) {
@@ -491,7 +557,7 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     }
     const uint64_t span_start = uint64_t(first) * p.sub_bits;                          // multiple of 128 bits
     const uint32_t span_bits = nthr * p.sub_bits;
-    load_dec_tabs(p.tabs, &s_tabs);
+    load_dec_tabs(p.tabs, &s_tabs, p.nb, p.ny);
     load_span(p.ustream + img * p.uslot, span_start / 8, span_bits / 8, p.uslot, s_span);
     const uint32_t span_sa = uint32_t(__cvta_generic_to_shared(s_span));
     const uint32_t start = uint32_t(isub - int64_t(first)) * p.sub_bits, end = start + p.sub_bits;   // relative to the span
@@ -640,7 +706,7 @@ __global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p)
     const uint64_t cta_start = uint64_t(blockIdx.x) * p.cta_own * p.sub_bits;
     if (cta_start >= total_bits) return;
     const uint32_t span_bits = p.cta_own * p.sub_bits;
-    load_dec_tabs(p.tabs, &s_tabs);
+    load_dec_tabs(p.tabs, &s_tabs, p.nb, p.ny);
     load_span(p.ustream + img * p.uslot, cta_start / 8, span_bits / 8, p.uslot, s_span);
     const uint32_t span_sa = uint32_t(__cvta_generic_to_shared(s_span));
     const uint32_t i = blockIdx.x * p.cta_own + threadIdx.x;
@@ -673,7 +739,7 @@ __global__ void __launch_bounds__(128) k_decode_segments(const DecParams p)
 {
     pdl_wait();
     __shared__ __align__(16) DecTabs s_tabs;
-    load_dec_tabs(p.tabs, &s_tabs);
+    load_dec_tabs(p.tabs, &s_tabs, p.nb, p.ny);
     __syncthreads();
     const size_t img = blockIdx.y;
     const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
