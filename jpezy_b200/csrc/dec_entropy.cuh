@@ -64,9 +64,9 @@ static_assert(sizeof(HuffSlow) % 4 == 0 && sizeof(HuffDecTab) % 16 == 0, "copied
 struct DecTabs {
     uint32_t fast[4][1 << kLutBits];
     HuffSlow slow[4];
-    // per block b of the MCU (decode_span): x = shared address of the AC table of block b; y = shared address of the DC table of the
-    // block after b (low 24 bits) | index of that block << 24
-    uint2 binfo[16];
+    // per block position b of the MCU (decode_span): x = shared address of the AC table of block b, y = shared address of the DC table
+    // of the block after b, z = shared address of the record of that block, w = b
+    uint4 binfo[16];
 };
 
 struct DecParams {
@@ -244,22 +244,20 @@ __device__ __forceinline__ void decode_span(FastBits& br, uint32_t& b, uint32_t&
     asm volatile("mov.u32 %0, %1;" : "=r"(tab) : "r"(uint32_t(__cvta_generic_to_shared(&T->fast[0][0]))));
     asm volatile("mov.u32 %0, %1;" : "=r"(binfo) : "r"(uint32_t(__cvta_generic_to_shared(&T->binfo[0]))));
     constexpr uint32_t kTab = 4u << kLutBits;                          // bytes per table
+    static_assert(kLutBits == 10, "the shift count in the step below");
     uint32_t w0 = br.hi, w1 = br.lo, w2 = br.nx, wa = br.wa, acc = br.acc, pk = br.pk, pos = br.pos;
-    uint32_t t_cont, t_new, bn;
-    {
-        uint2 bi;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bi.x), "=r"(bi.y) : "r"(binfo + 8u * b));
-        t_cont = bi.x, t_new = bi.y & 0xffffffu, bn = bi.y >> 24;
-    }
+    // the record of the current block position: AC table of this block, DC table of the next block, record of the next block
+    uint32_t pb = binfo + 16u * b, t_cont, t_new, pbn;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%3];\n\tld.shared.u32 %2, [%3+8];" : "=r"(t_cont), "=r"(t_new), "=r"(pbn) : "r"(pb));
     uint32_t e = lds32((z == 0u ? t_cont - 2u * kTab : t_cont) + ((pk >> (32 - kLutBits)) << 2));
-    for (;;) {
+    // one symbol; returns 0 = go on, 1 = the span is done, 2 = not a plain symbol (nothing committed)
+    auto step = [&]() -> int {
         const uint32_t dz = __byte_perm(e, 0, 0x4441);
         const uint32_t zs = z + dz;
-        // speculative consume (into temporaries) and the load of the next entry
         const uint32_t a2 = acc + e;
         const bool endb = zs >= 64u;
         const uint32_t tsel = endb ? t_new : t_cont;
-        // (spelled out: left to itself the compiler predicates the second shift on the crossing test and puts three more
+        // (spelled out: left to itself the compiler puts the word-boundary test in front of the shift and three more
         // instructions on the chain)
         uint32_t pk2, en, crossw;
         asm volatile(
@@ -276,32 +274,10 @@ __device__ __forceinline__ void decode_span(FastBits& br, uint32_t& b, uint32_t&
             : "=r"(pk2), "=r"(en), "=r"(crossw)
             : "r"(a2), "r"(acc), "r"(w0), "r"(w1), "r"(w2), "r"(tsel)
             : "memory");
-        static_assert(kLutBits == 10, "the shift count above");
         const bool cross = crossw != 0u;
         uint32_t w3 = w2;
         if (cross) w3 = lds32(wa);
-        if (zs >= 128u) {          // not a plain symbol (nothing has been committed yet)
-            const uint32_t t_cur = z == 0u ? t_cont - 2u * kTab : t_cont;
-            if (dz == 255u) {      // code longer than kLutBits, or none
-                e = huff_lookup_slow(T->slow + ((t_cur - tab) / kTab), pk);
-                if (e == 0u) {     // no such code: only legal while speculating.  One bit is dropped, the state stays
-                    if (kWrite && corrupt) *corrupt = 1;
-                    const uint32_t a1 = acc + 1u;
-                    if ((a1 ^ acc) & 32u) {
-                        w0 = w1, w1 = w2, w2 = lds32(wa);
-                        wa += 4u;
-                    }
-                    acc = a1;
-                    pk = __funnelshift_l(w1, w0, a1);
-                    pos += 1u;
-                    e = lds32(t_cur + ((pk >> (32 - kLutBits)) << 2));
-                    if (pos >= stop) break;
-                }
-            } else {               // the symbol fills the block itself: the bits that look like EOB are the next block's
-                e = unfold_entry(e);
-            }
-            continue;
-        }
+        if (zs >= 128u) return 2;
         // commit
         const uint32_t w = pk;
         w0 = cross ? w1 : w0, w1 = cross ? w2 : w1, w2 = w3;
@@ -322,18 +298,43 @@ __device__ __forceinline__ void decode_span(FastBits& br, uint32_t& b, uint32_t&
             }
         }
         z = endb ? 0u : zs;
-        b = endb ? bn : b;
+        pb = endb ? pbn : pb;
         nblocks += endb ? 1u : 0u;
         blk += endb ? 1u : 0u;
         e = en;
-        if (kWrite && blk >= nblk) break;
-        {
-            uint2 bi;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bi.x), "=r"(bi.y) : "r"(binfo + 8u * b));
-            t_cont = bi.x, t_new = bi.y & 0xffffffu, bn = bi.y >> 24;
+        if (kWrite && blk >= nblk) return 1;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%3];\n\tld.shared.u32 %2, [%3+8];" : "=r"(t_cont), "=r"(t_new), "=r"(pbn) : "r"(pb));
+        return pos >= stop ? 1 : 0;
+    };
+    for (;;) {
+        int r;
+        for (;;) {             // (two symbols per trip: the compiler renames the loop-carried values instead of copying them)
+            if ((r = step())) break;
+            if ((r = step())) break;
         }
-        if (pos >= stop) break;
+        if (r == 1) break;
+        // not a plain symbol
+        const uint32_t t_cur = z == 0u ? t_cont - 2u * kTab : t_cont;
+        if ((e & 0xff00u) == 0xff00u) {      // code longer than kLutBits, or none
+            e = huff_lookup_slow(T->slow + ((t_cur - tab) / kTab), pk);
+            if (e == 0u) {     // no such code: only legal while speculating.  One bit is dropped, the state stays
+                if (kWrite && corrupt) *corrupt = 1;
+                const uint32_t a1 = acc + 1u;
+                if ((a1 ^ acc) & 32u) {
+                    w0 = w1, w1 = w2, w2 = lds32(wa);
+                    wa += 4u;
+                }
+                acc = a1;
+                pk = __funnelshift_l(w1, w0, a1);
+                pos += 1u;
+                e = lds32(t_cur + ((pk >> (32 - kLutBits)) << 2));
+                if (pos >= stop) break;
+            }
+        } else {               // the symbol fills the block itself: the bits that look like EOB are the next block's
+            e = unfold_entry(e);
+        }
     }
+    b = lds32(pb + 12u);
     br.hi = w0, br.lo = w1, br.nx = w2, br.wa = wa, br.acc = acc, br.pk = pk, br.pos = pos;
 }
 
@@ -342,7 +343,8 @@ __device__ __forceinline__ void load_dec_tabs(const HuffDecTab* __restrict__ tab
     if (threadIdx.x < 16) {
         const uint32_t b = threadIdx.x, bn = b + 1u >= nb ? 0u : b + 1u;
         const uint32_t base = uint32_t(__cvta_generic_to_shared(&T->fast[0][0]));
-        T->binfo[b] = make_uint2(base + (2u + (b >= ny ? 1u : 0u)) * (4u << kLutBits), (base + (bn >= ny ? 1u : 0u) * (4u << kLutBits)) | (bn << 24));
+        T->binfo[b] = make_uint4(base + (2u + (b >= ny ? 1u : 0u)) * (4u << kLutBits), base + (bn >= ny ? 1u : 0u) * (4u << kLutBits),
+                                 uint32_t(__cvta_generic_to_shared(&T->binfo[bn])), b);
     }
     constexpr int kFast16 = (1 << kLutBits) * 4 / 16, kSlowW = int(sizeof(HuffSlow) / 4);
     // eight loads in flight per thread: the tables come out of L2 at its latency, not at eight times that
