@@ -70,9 +70,10 @@ enum {
                                      0 (default) = the reference's own bound, 3 bytes per pixel of the shard.  A shard that does
                                      not fit makes EVERY rank report overflow in phase D (no silently short segment) */
     JPEZYB200_OPT_SYNC_ROUNDS = 3 /* self-synchronisation launches enqueued after the first one by the
-                                     decoder: n > 0 = exactly n, no host round trip (default 3; one is
-                                     needed on ordinary streams thanks to the warm-up overlap, later ones return at once); 0 = the
-                                     host polls a device flag after every launch until the fixed point */
+                                     decoder: n > 0 = exactly n, no host round trip (default 2; the first launch checks
+                                     the boundaries of its thread blocks itself, so on ordinary streams none of them has work and
+                                     all return at once); 0 = the host polls a device flag after every launch until the fixed
+                                     point */
 };
 JPEZYB200_API int jpezyb200_set_option(jpezyb200_ctx* ctx, int option, int64_t value);
 

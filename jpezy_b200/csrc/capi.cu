@@ -188,7 +188,7 @@ void jpezyb200_ctx_destroy(jpezyb200_ctx* ctx)
     jz_devbuf* bufs[] = {&ctx->coefs, &ctx->blk_off, &ctx->tile_sum, &ctx->tile_base, &ctx->img_bits, &ctx->ustream,
                          &ctx->ff_sum, &ctx->ff_base, &ctx->planes_in, &ctx->planes_out, &ctx->scan_io, &ctx->sizes_io,
                          &ctx->dec_scanbytes, &ctx->dec_chunk_cnt, &ctx->dec_chunk_base, &ctx->dec_ubytes, &ctx->dec_state,
-                         &ctx->dec_dirty, &ctx->dec_subblk, &ctx->dec_dc, &ctx->dec_dcd, &ctx->blk_meta, &ctx->dec_status, &ctx->dec_changed, &ctx->shard_geom, &ctx->dec_mcnt, &ctx->dec_mbase, &ctx->dec_seg};
+                         &ctx->dec_dirty, &ctx->dec_subblk, &ctx->dec_dc, &ctx->dec_dcd, &ctx->blk_meta, &ctx->dec_status, &ctx->dec_changed, &ctx->dec_flags, &ctx->shard_geom, &ctx->dec_mcnt, &ctx->dec_mbase, &ctx->dec_seg};
     for (jz_devbuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_enc_lut) cudaFree(ctx->d_enc_lut);

@@ -99,7 +99,7 @@ struct jpezyb200_ctx {
     std::string err;
     int pad_ones = 1;
     int transform_variant = 0;
-    int sync_rounds = 3;
+    int sync_rounds = 2;      // launches behind launch 0 (which checks the CTA boundaries itself): one that repairs, one that verifies
     int64_t shard_scratch = 0;                 // JPEZYB200_OPT_SHARD_SCRATCH_BYTES (0 = 3 bytes per pixel)
     int64_t group_bytes = int64_t(96) << 20;   // host<->device bytes per stage of the pipelined host batches
     uint64_t launches = 0;
@@ -122,7 +122,7 @@ struct jpezyb200_ctx {
 
     // scratch
     jz_devbuf coefs, blk_off, tile_sum, tile_base, img_bits, ustream, ff_sum, ff_base, planes_in, planes_out, scan_io, sizes_io;
-    jz_devbuf dec_scanbytes, dec_chunk_cnt, dec_chunk_base, dec_ubytes, dec_state, dec_dirty, dec_subblk, dec_dc, dec_dcd, blk_meta, dec_status, dec_changed, dec_mcnt, dec_mbase, dec_seg;
+    jz_devbuf dec_scanbytes, dec_chunk_cnt, dec_chunk_base, dec_ubytes, dec_state, dec_dirty, dec_subblk, dec_dc, dec_dcd, blk_meta, dec_status, dec_changed, dec_flags, dec_mcnt, dec_mbase, dec_seg;
     jz_devbuf shard_geom;      // ShardGeom + scratch of the MCU-row sharded encoder (enc_shard.cuh)
     void* batch_pipe = nullptr;    // streams, events and double buffers of the pipelined host batches (capi_batch.inc)
     void* host_pipe = nullptr;     // copy stream and events of the band-pipelined single-image host entry points (capi.cu)

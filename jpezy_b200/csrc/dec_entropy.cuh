@@ -106,7 +106,10 @@ struct DecParams {
     uint32_t* state_a;        // [nimg][ncta] CTA tail states, double buffered across launches
     uint32_t* state_b;
     uint32_t* sub_blk;        // [nimg][nsub] exclusive prefix of block counts
-    unsigned long long* changed;   // [rounds + 1] number of end states that changed in launch k (k >= 1); zeroed per call
+    unsigned long long* changed;   // [rounds + 1] number of end states that changed in launch k (k >= 1); [0]: CTA boundaries at which
+                                   // launch 0 found its warm-up result different from the previous CTA's tail; zeroed per call
+    uint32_t* cta_flag;            // [nimg][ncta] set when a CTA of launch 0 has published its tail; zeroed per call (k_unstuff_count)
+    uint32_t nflag;                // nimg * ncta
     uint32_t rounds;          // launches 1..rounds of k_sync_decode are enqueued after launch 0
     uint32_t rounds_host;     // launches the host-driven loop needed (rounds == 0)
     unsigned long long* rounds_stat;   // receives the number of launches that did work
@@ -441,6 +444,8 @@ __global__ void __launch_bounds__(kDecThreads) k_unstuff_count(const DecParams p
         if (threadIdx.x < kMaxSyncRounds) p.changed[threadIdx.x] = 0;
         if (threadIdx.x < 2) p.iters_stat[threadIdx.x] = 0;
     }
+    if (p.cta_flag)
+        for (uint32_t i = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < p.nflag; i += gridDim.x * gridDim.y * blockDim.x) p.cta_flag[i] = 0;
     uint64_t n = p.ext_bytes ? p.ext_bytes[img] : (p.ninline ? p.inline_bytes[img & 7] : p.scan_bytes[img]);
     if (p.ext_bytes && n > p.max_bytes) n = 0;       // does not fit what the launch was sized for: nothing is decoded (k_scan_blocks reports it)
     if ((p.ninline || p.ext_bytes) && blockIdx.x == 0 && threadIdx.x == 0) const_cast<uint64_t*>(p.scan_bytes)[img] = n;
@@ -529,8 +534,12 @@ __global__ void __launch_bounds__(kDecThreads) k_unstuff_write(const DecParams p
 // state (b = 0, z = 0); then the CTA iterates in shared memory: a thread whose predecessor's end state changed
 // re-decodes from it, until nothing changes inside the CTA.  Huffman codes re-synchronise within a few subsequences, so
 // by the end of the warm-up run the states are the true ones and the owned subsequences come out right in launch 0.
+// Launch 0 ends with a check across the CTA boundary: the CTA's own (warm-up) end state of the subsequence in front of its
+// first owned one against the previous CTA's tail.  If they agree at every boundary, every CTA's owned states follow from its
+// predecessor's tail, and by induction from CTA 0 (which starts at the beginning of the stream) all of them are the true ones:
+// changed[0] stays 0 and the launches behind return at once.
 // Launch k >= 1: the first owned subsequence is re-seeded from the previous CTA's last end state of launch k - 1
-// (`tail`); `changed` counts the end states that changed during a launch, 0 = global fixed point (normally launch 1).
+// (`tail`); `changed` counts the end states that changed during a launch, 0 = global fixed point.
 constexpr int kDecWarm = 32;
 
 __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, const int launch, const int host_poll)
@@ -545,7 +554,7 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     // launches are enqueued without host round trips: once a launch saw no change (a global fixed point), the
     // later ones return immediately (changed[] stays 0 for them, so the zero propagates to changed[rounds])
     // (host_poll: the host reads changed[1] after every launch instead)
-    if (!host_poll && launch >= 2 && p.changed[launch - 1] == 0) return;
+    if (!host_poll && launch >= 1 && p.changed[launch - 1] == 0) return;
     const size_t img = blockIdx.y;
     const uint64_t total_bits = p.ubytes[img] * 8;
     const int t = threadIdx.x;
@@ -651,6 +660,24 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     const bool is_tail = mine && (t == int(nthr) - 1 || end >= limit || isub + 1 >= int64_t(p.nsub));
     if (is_tail) tail_out[img * ncta + blockIdx.x] = st;
     if (launch > 0 && nchanged) atomicAdd(p.changed + (host_poll ? 1 : launch), (unsigned long long)nchanged);
+    if (launch == 0 && p.cta_flag) {
+        // (a CTA only ever waits for the CTA in front of it, which was scheduled no later: no deadlock)
+        volatile uint32_t* flag = p.cta_flag + img * ncta;
+        if (is_tail) {
+            __threadfence();
+            flag[blockIdx.x] = 1u;
+        }
+        if (t == kDecWarm - 1 && blockIdx.x > 0) {
+            uint32_t spins = 0;
+            while (flag[blockIdx.x - 1] == 0u) {
+                __nanosleep(64);
+                if (++spins > (1u << 24)) __trap();      // (a protocol error must not hang the device)
+            }
+            __threadfence();
+            const uint32_t ps = *(volatile uint32_t*)(tail_out + img * ncta + blockIdx.x - 1);
+            if ((ps ^ st) & kStateSyncMask) atomicAdd(p.changed, 1ull);
+        }
+    }
     // blocks completed inside this CTA's own subsequences (input of the block-index scan)
     uint32_t total;
     cta_scan_excl(mine ? (st >> 15) & 4095u : 0u, reinterpret_cast<uint32_t*>(s_state), &total);
@@ -689,7 +716,7 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(const DecParams p, const u
         }
         if (img == 0) {
             unsigned long long n = 1 + p.rounds_host;
-            for (uint32_t k = 1; k <= p.rounds; ++k) n += (k == 1 || p.changed[k - 1] != 0) ? 1ull : 0ull;
+            for (uint32_t k = 1; k <= p.rounds; ++k) n += p.changed[k - 1] != 0 ? 1ull : 0ull;
             *p.rounds_stat = n;
         }
     }

@@ -178,8 +178,9 @@ def test_sync_round_modes_agree(ctx, oracle):
                     assert (got[0] == want).all()
             else:
                 assert st[0] == 0 and (got[0] == want).all()
-                assert ctx.stat(capi.STAT_SYNC_ROUNDS) >= 2
+                # launch 0 alone when its check across the CTA boundaries found every warm-up result equal to the previous CTA's tail
+                assert ctx.stat(capi.STAT_SYNC_ROUNDS) >= (2 if rounds == 0 else 1)
             R, G, B = ctx.decode(split(f), J.default_frame(W, H))      # host entry point: always completes
             assert (R == R0).all() and (G == G0).all() and (B == B0).all()
     finally:
-        ctx.set_option(capi.OPT_SYNC_ROUNDS, 3)
+        ctx.set_option(capi.OPT_SYNC_ROUNDS, 2)
