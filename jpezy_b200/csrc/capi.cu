@@ -93,6 +93,7 @@ int jpezyb200_ctx_create(int device, jpezyb200_ctx** out)
     jpezyb200_ctx* ctx = new (std::nothrow) jpezyb200_ctx();
     if (!ctx) return JPEZYB200_ENOMEM;
     ctx->device = device;
+    if (const char* e = std::getenv("JPEZY_B200_SYNC_ROUNDS")) ctx->sync_rounds = std::atoi(e);      // (debugging: JPEZYB200_OPT_SYNC_ROUNDS of every new context)
     int rc = [&]() -> int {
         JZ_CUDA_TRY(ctx, cudaSetDevice(device));
         JZ_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));

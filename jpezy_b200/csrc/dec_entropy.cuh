@@ -684,6 +684,194 @@ __global__ void __launch_bounds__(kDecThreads) k_sync_decode(const DecParams p, 
     if (t == 0) p.sub_blk[img * ncta + blockIdx.x] = total;
 }
 
+// ---- D1a, launch 0 for latency-bound inputs (a single frame): several guesses per subsequence -----------------------------
+// How long the chain of dependent re-decodes of k_sync_decode gets is set by the slowest synchronisation anywhere in the
+// image: position and zig-zag index of a decoder started from a guess merge with the true parse within a few symbols, but its
+// block-in-MCU phase only re-rolls about once per MCU, and the tail of that distribution is long (tools/sync_distance_sim.py on
+// a 4K S-photo frame: up to 12+ subsequences of 128 bits for the single guess b = 0, at most 5 -- 99.9 %: at most 3 -- for the
+// best of the guesses b = 0..nb-1).  So this kernel runs one chain per guess, nb x as many threads, all at once:
+//   round 0       thread (slot, h) decodes its subsequence from the state (block h, start of block);
+//   rounds 1..K   ... again from the end state of (slot - 1, h) of the round before, unless that is what it used last time;
+//   walk          from an anchor (the start of the image, or the last warm-up slot at which all chains agree) the true state is
+//                 carried from slot to slot: E_slot(x) is looked up among the inputs the slot's chains were decoded from, and
+//                 decoded only on a miss.
+// What comes out are the states k_sync_decode would reach (same arrays, same check against the previous CTA's tail at the end,
+// so a wrong anchor is caught and repaired by launch 1): the guesses only decide how fast.
+constexpr int kHypRounds = 2;
+constexpr int kHypOwn = 64;         // subsequences a CTA owns (DecParams::cta_own on this path)
+constexpr int kHypWarm = 16;        // warm-up subsequences in front of them: enough to find a slot at which all chains agree
+constexpr int kHypSlots = kHypOwn + kHypWarm;
+constexpr int kHypMax = 6;          // blocks per MCU = guesses
+
+__global__ void __launch_bounds__(kHypSlots * kHypMax, 2) k_sync_decode_hyp(const DecParams p)
+{
+    pdl_wait();
+    extern __shared__ __align__(16) uint32_t s_span[];
+    __shared__ __align__(16) DecTabs s_tabs;
+    __shared__ uint32_t s_v[kHypMax][kHypSlots];       // end state of chain h at the slot
+    __shared__ uint32_t s_in[kHypMax][kHypSlots];      // the state it was decoded from (0xffffffff: its guess)
+    __shared__ uint32_t s_state[kHypSlots];
+    __shared__ uint8_t s_una[kHypSlots];
+    __shared__ uint16_t s_work[kHypSlots * kHypMax];   // work list of a round: slot | chain << 8
+    __shared__ uint32_t s_nwork;
+    __shared__ uint32_t s_scan[32];
+    const size_t img = blockIdx.y;
+    const uint64_t total_bits = p.ubytes[img] * 8;
+    const int t = threadIdx.x;
+    constexpr uint32_t slots = uint32_t(kHypSlots);                                      // blockDim.x == slots * p.nb; p.cta_own == kHypOwn
+    const uint32_t h = uint32_t(t) / slots, slot = uint32_t(t) - h * slots;
+    const uint32_t first_own = blockIdx.x * p.cta_own;
+    const uint32_t s0 = blockIdx.x == 0 ? uint32_t(kHypWarm) : 0u;                       // slot of the first subsequence of the span
+    const uint32_t first = first_own - (uint32_t(kHypWarm) - s0);
+    const int64_t isub = int64_t(first_own) - kHypWarm + slot;
+    if (uint64_t(first_own) * p.sub_bits >= total_bits) {     // (capacity CTA beyond the data of this image)
+        if (t == 0) p.sub_blk[img * gridDim.x + blockIdx.x] = 0;
+        return;
+    }
+    const uint64_t span_start = uint64_t(first) * p.sub_bits;
+    const uint32_t span_bits = slots * p.sub_bits;
+    load_dec_tabs(p.tabs, &s_tabs, p.nb, p.ny);
+    load_span(p.ustream + img * p.uslot, span_start / 8, span_bits / 8, p.uslot, s_span);
+    const uint32_t span_sa = uint32_t(__cvta_generic_to_shared(s_span));
+    const uint32_t start = (slot - s0) * p.sub_bits, end = start + p.sub_bits;           // (meaningless for slot < s0: not valid)
+    const uint32_t limit = uint32_t(min(total_bits - span_start, uint64_t(span_bits) + 256u));
+    const bool owner = slot >= uint32_t(kHypWarm);
+    const bool valid = isub >= 0 && isub < int64_t(p.nsub) && start < limit;
+    const size_t si = img * p.nsub + size_t(isub < 0 ? 0 : isub);
+    const uint32_t ncta = gridDim.x;
+    uint32_t* tail_out = p.state_b;                             // (launch 0 of k_sync_decode writes state_b)
+    if (t == 0) s_nwork = 0;
+    __syncthreads();
+
+    auto decode_from = [&](uint32_t at, uint32_t ps) -> uint32_t {
+        FastBits br;
+        br.init(span_sa, at + (ps & 63u));
+        uint32_t b = (ps >> 6) & 7u, z = (ps >> 9) & 63u, n = 0;
+        decode_span<false>(br, b, z, n, at + p.sub_bits, limit, &s_tabs, nullptr, nullptr, 0, 0, nullptr, p.nb, p.ny);
+        return pack_state(br.pos > at + p.sub_bits ? br.pos - (at + p.sub_bits) : 0u, b, z, n);
+    };
+
+    // ---- round 0: from the guesses (the first subsequence of the image has no guess: block 0, start of block, is the truth) ----
+    uint32_t vin = 0xffffffffu;
+    s_v[h][slot] = valid ? decode_from(start, isub == 0 ? 0u : (h << 6)) : 0u;
+    // ---- rounds 1..K: every chain one subsequence further.  Chains that have merged give their successors the same input: one
+    //      thread per distinct (slot, input) decodes -- the work items are compacted so that a round costs as many warps as it has
+    //      work -- and the others copy; an input that did not change since the last round needs nothing. ----
+    const bool has_pred = valid && isub > 0 && slot > 0;
+#pragma unroll 1
+    for (int k = 1; k <= kHypRounds; ++k) {
+        __syncthreads();
+        uint32_t in = 0xffffffffu, rep = h;
+        bool work = false;
+        if (has_pred) {
+            in = s_v[h][slot - 1];
+            for (uint32_t a = 0; a < h; ++a)
+                if (((s_v[a][slot - 1] ^ in) & kStateSyncMask) == 0u) {
+                    rep = a;
+                    break;
+                }
+            work = rep == h && ((in ^ vin) & kStateSyncMask) != 0u;
+        }
+        {
+            const uint32_t bal = __ballot_sync(0xffffffffu, work);
+            uint32_t wbase = 0;
+            if ((t & 31) == 0 && bal) wbase = atomicAdd(&s_nwork, uint32_t(__popc(bal)));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (work) s_work[wbase + __popc(bal & ((1u << (t & 31)) - 1u))] = uint16_t(slot | (h << 8));
+        }
+        __syncthreads();
+        const uint32_t nwork = s_nwork;
+        uint32_t it_slot = 0, it_h = 0, res = 0;
+        if (uint32_t(t) < nwork) {
+            const uint32_t item = s_work[t];
+            it_slot = item & 255u, it_h = item >> 8;
+            res = decode_from((it_slot - s0) * p.sub_bits, s_v[it_h][it_slot - 1]);
+        }
+        __syncthreads();                 // every read of the previous round's states is done
+        if (uint32_t(t) < nwork) s_v[it_h][it_slot] = res;
+        if (t == 0) s_nwork = 0;
+        __syncthreads();
+        if (has_pred) {
+            // a follower takes its representative's state (the representative's own, if its input did not change, is still the one
+            // that belongs to this input)
+            if (rep != h) s_v[h][slot] = s_v[rep][slot];
+            vin = in;
+        }
+    }
+    __syncthreads();
+    s_in[h][slot] = vin;
+    if (h == 0) {
+        // all chains in the same state: the true one (a decoder that has merged with another stays merged, and the true parse is one
+        // of the decoders; nb chains that agree with each other but not with it would have had to merge without touching it)
+        bool una = valid;
+        for (uint32_t a = 1; a < p.nb; ++a) una = una && ((s_v[a][slot] ^ s_v[0][slot]) & kStateSyncMask) == 0u;
+        s_una[slot] = una ? 1 : 0;
+        s_state[slot] = s_v[0][slot];
+    }
+    __syncthreads();
+    // ---- the true chain: from an anchor -- the start of the image, or the last warm-up slot whose chains all agree -- follow
+    //      E_slot(x) through the slots; it is looked up among the inputs the slot's chains were decoded from (a hit is a few
+    //      shared-memory reads by the lanes of one warp, and supplies the block count that goes with the TRUE input) and decoded
+    //      only on a miss.  One warp walks, the others wait: ~40 cycles per slot. ----
+    if (t < 32) {
+        const uint32_t lane = uint32_t(t);
+        int w = int(kHypWarm) - 1;                                                       // anchor slot
+        if (blockIdx.x == 0) w = int(kHypWarm);
+        else {
+            const uint32_t bal = __ballot_sync(0xffffffffu, lane < uint32_t(kHypWarm) && s_una[lane] != 0);
+            if (bal) w = 31 - __clz(int(bal));
+        }
+        uint32_t x = s_state[w];
+        uint32_t misses = 0;
+        for (uint32_t ts = uint32_t(w) + 1u; ts < slots; ++ts) {
+            const uint32_t start_ts = (ts - s0) * p.sub_bits;
+            if (start_ts >= limit || int64_t(first_own) - kHypWarm + ts >= int64_t(p.nsub)) break;
+            const uint32_t key = lane < p.nb ? s_in[lane][ts] : 0xffffffffu;
+            const uint32_t val = lane < p.nb ? s_v[lane][ts] : 0u;
+            const uint32_t hit = __ballot_sync(0xffffffffu, key != 0xffffffffu && ((key ^ x) & kStateSyncMask) == 0u);
+            if (hit) {
+                x = __shfl_sync(0xffffffffu, val, __ffs(int(hit)) - 1);
+            } else {
+                if (lane == 0) x = decode_from(start_ts, x);
+                x = __shfl_sync(0xffffffffu, x, 0);
+                ++misses;
+            }
+            if (lane == 0) s_state[ts] = x;
+        }
+        if (lane == 0) {
+            atomicMax(p.iters_stat, (unsigned long long)(misses + kHypRounds));
+            atomicAdd(p.iters_stat + 1, (unsigned long long)misses);
+        }
+    }
+    __syncthreads();
+    // ---- results: as k_sync_decode, by the threads of chain 0 ----
+    const uint32_t st = h == 0 ? s_state[slot] : 0u;
+    const bool mine = h == 0 && valid && owner;
+    if (mine) p.sub_state[si] = st;
+    const bool is_tail = mine && (slot == slots - 1 || end >= limit || isub + 1 >= int64_t(p.nsub));
+    if (is_tail) tail_out[img * ncta + blockIdx.x] = st;
+    if (p.cta_flag) {
+        volatile uint32_t* flag = p.cta_flag + img * ncta;
+        if (is_tail) {
+            __threadfence();
+            flag[blockIdx.x] = 1u;
+        }
+        if (h == 0 && slot == uint32_t(kHypWarm) - 1u && blockIdx.x > 0) {
+            uint32_t spins = 0;
+            while (flag[blockIdx.x - 1] == 0u) {
+                __nanosleep(64);
+                if (++spins > (1u << 24)) __trap();
+            }
+            __threadfence();
+            const uint32_t ps = *(volatile uint32_t*)(tail_out + img * ncta + blockIdx.x - 1);
+            if ((ps ^ st) & kStateSyncMask) atomicAdd(p.changed, 1ull);
+        }
+    }
+    uint32_t total;
+    cta_scan_excl(mine ? (st >> 15) & 4095u : 0u, s_scan, &total);
+    if (t == 0) p.sub_blk[img * ncta + blockIdx.x] = total;
+}
+
 // exclusive scan of the per-CTA block counts (in place) and per-image status
 __global__ void __launch_bounds__(1024) k_scan_blocks(const DecParams p, const uint32_t ncta)
 {
@@ -758,7 +946,9 @@ __global__ void __launch_bounds__(kDecThreads) k_write_coefs(const DecParams p)
     br.init(span_sa, pos);
     int corrupt = 0;
     decode_span<true>(br, b, z, n, start + p.sub_bits, limit, &s_tabs, p.coefs + img * p.coef_stride, p.dcd + img * p.nblk, blk, p.nblk, &corrupt, p.nb, p.ny);
-    if (corrupt && p.status) p.status[img] = JPEZYB200_ECORRUPT;
+    // (only over "ok": when the synchronisation did not converge -- JPEZYB200_EAGAIN from k_scan_blocks -- this pass ran from wrong
+    // states, and what it saw says nothing about the stream: the caller decodes again)
+    if (corrupt && p.status) atomicCAS(p.status + img, 0, int(JPEZYB200_ECORRUPT));
 }
 
 // ---- restart intervals: every segment is self-contained (predictors reset, byte aligned), one thread each --------

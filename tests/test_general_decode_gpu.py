@@ -74,6 +74,22 @@ def test_general_baseline_decode_matches_reference_decoder(tmp_path, oracle, nam
         assert q.returncode == 0 and (tmp_path / "ref.ppm").read_text() == out.read_text()
 
 
+def test_decode_again_when_the_enqueued_synchronisation_launches_were_not_enough(tmp_path, oracle):
+    """a high-quality file needs more self-synchronisation launches than a context that enqueues a single one provides: the device
+    reports JPEZYB200_EAGAIN and jpezyb200_decode decodes again with the host-polled loop.  (The writing pass of the first attempt
+    runs from wrong states and trips over impossible runs; that must not turn "again" into "corrupt".)"""
+    W, H = 640, 360
+    f = jpeg_bytes(picture(W, H, 7), "L", quality=100)
+    jpg, out = tmp_path / "in.jpg", tmp_path / "out.ppm"
+    jpg.write_bytes(f)
+    Wd, Hd, R0, G0, B0 = oracle.decode(f)
+    env = dict(os.environ, JPEZY_B200_SYNC_ROUNDS="1")
+    p = subprocess.run([DEC, str(jpg), str(out)], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    vals = np.array(" ".join(out.read_text().split("\n")[4:]).split(), dtype=np.int64).reshape(-1, 3)
+    assert (vals[:, 0] == R0[: W * H]).all() and (vals[:, 1] == G0[: W * H]).all() and (vals[:, 2] == B0[: W * H]).all()
+
+
 DRI_CASES = [("420_dri2", "RGB", dict(quality=75, subsampling=2, restart_marker_blocks=2)),
              ("444_dri_row", "RGB", dict(quality=80, subsampling=0, restart_marker_rows=1)),
              ("422_dri7", "RGB", dict(quality=50, subsampling=1, restart_marker_blocks=7)),
