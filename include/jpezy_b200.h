@@ -70,7 +70,7 @@ enum {
                                      0 (default) = the reference's own bound, 3 bytes per pixel of the shard.  A shard that does
                                      not fit makes EVERY rank report overflow in phase D (no silently short segment) */
     JPEZYB200_OPT_SYNC_ROUNDS = 3 /* self-synchronisation launches enqueued after the first one by the
-                                     decoder: n > 0 = exactly n, no host round trip (default 2; the first launch checks
+                                     decoder: n > 0 = exactly n, no host round trip (default 3; the first launch checks
                                      the boundaries of its thread blocks itself, so on ordinary streams none of them has work and
                                      all return at once); 0 = the host polls a device flag after every launch until the fixed
                                      point */

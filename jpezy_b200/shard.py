@@ -283,7 +283,7 @@ class ShardedDecoder:
                                           self.base + 2 * pl, pl, self.status, stream=stream)
                 self.torch.cuda.synchronize()
             finally:
-                self.ctx.set_option(capi.OPT_SYNC_ROUNDS, 2)
+                self.ctx.set_option(capi.OPT_SYNC_ROUNDS, 3)
         self.group.barrier()
         self.torch.cuda.synchronize()
         if int(self.status.item()):

@@ -183,4 +183,4 @@ def test_sync_round_modes_agree(ctx, oracle):
             R, G, B = ctx.decode(split(f), J.default_frame(W, H))      # host entry point: always completes
             assert (R == R0).all() and (G == G0).all() and (B == B0).all()
     finally:
-        ctx.set_option(capi.OPT_SYNC_ROUNDS, 2)
+        ctx.set_option(capi.OPT_SYNC_ROUNDS, 3)
