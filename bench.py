@@ -537,6 +537,7 @@ def main():
     ap.add_argument("--shard", action="store_true", help="c4 under torchrun: ONE image split by MCU rows over the ranks (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-lanes", type=int, default=2, help="host pipelines (encode thread + decode thread each) run side by side in the e2e measurement")
     ap.add_argument("--no-configs", action="store_true", help="skip the c3 / c5 / c4_shard measurements appended to the default line")
     ap.add_argument("--host-lengths", action="store_true", help="segment lengths through a host array between encoder and decoder (round-1 step)")
     args = ap.parse_args()
@@ -785,71 +786,99 @@ def main():
         # The same calls as a two-stage pipeline: while step i is decoded (device -> host is the long copy), step i + 1 is
         # encoded (host -> device is the long copy) by a second host thread on a second context -- PCIe is full duplex and
         # a context is used by one thread at a time (SURVEY.md 8b "Threading").  Every step still carries its own
-        # host-to-device copy of the input planes and device-to-host copy of the decoded planes.
-        ctx2 = J.Context(local_rank)
-        if B == 1:
-            hscan2 = [hscan, torch.empty_like(hscan).pin_memory()]
-            nb2 = [C.c_size_t(0), C.c_size_t(0)]
-
-            def enc_stage(i):
-                ctx._chk(L.jpezyb200_encode(ctx.h, hin[i % nh][0].data_ptr(), hin[i % nh][1].data_ptr(), hin[i % nh][2].data_ptr(), W, H,
-                                            int(gray), hscan2[i & 1].data_ptr(), hscan2[i & 1].numel(), C.byref(nb2[i & 1]), C.byref(nbits_c)))
-
-            def dec_stage(i):
-                ctx2._chk(L.jpezyb200_decode(ctx2.h, hscan2[i & 1].data_ptr(), nb2[i & 1].value, C.byref(frame), int(gray),
-                                             hout[0].data_ptr(), hout[1].data_ptr(), hout[2].data_ptr(), plane_len))
-        else:
-            hscan2 = [hscan, torch.empty_like(hscan).pin_memory()]
-            hnb2 = [hnb, np.zeros_like(hnb)]
-
-            def enc_stage(i):
-                ctx.encode_batch(hin[i % nh][0], hin[i % nh][1], hin[i % nh][2], W, H, B, gray, hscan2[i & 1], hslot, hnb2[i & 1])
-
-            def dec_stage(i):
-                ctx2.decode_batch(hscan2[i & 1], hslot, hnb2[i & 1], B, frame, gray, hout[0], hout[1], hout[2], plane_len, hst)
-                assert not hst.any()
+        # host-to-device copy of the input planes and device-to-host copy of the decoded planes.  --e2e-lanes L runs L such
+        # pipelines side by side (steps i = lane mod L; 2 L contexts, 2 L host threads), the way a transcoding host with several
+        # worker threads would: while one lane's kernels run, another lane's copies keep the two copy engines busy.
+        n_lanes = max(1, args.e2e_lanes)
         n_pipe = 2 * n_e2e
-        # two scan buffers between the stages: the encoder may run up to two steps ahead of the decoder
-        filled = [threading.Semaphore(0), threading.Semaphore(0)]
-        free = [threading.Semaphore(1), threading.Semaphore(1)]
+
+        class Lane:
+            def __init__(self, k):
+                self.k = k
+                self.ctx_e = ctx if k == 0 else J.Context(local_rank)
+                self.ctx_d = J.Context(local_rank)
+                self.hscan2 = [hscan if k == 0 else torch.empty_like(hscan).pin_memory(), torch.empty_like(hscan).pin_memory()]
+                self.hout = hout if k == 0 else [torch.empty_like(x).pin_memory() for x in hout]
+                self.nb2 = [C.c_size_t(0), C.c_size_t(0)]
+                self.nbits = C.c_uint64(0)
+                self.hnb2 = [np.zeros(B, dtype=np.uint64), np.zeros(B, dtype=np.uint64)]
+                self.hst = np.zeros(B, dtype=np.int32)
+                # two scan buffers between the stages: the encoder may run up to two steps ahead of the decoder
+                self.filled = [threading.Semaphore(0), threading.Semaphore(0)]
+                self.free = [threading.Semaphore(1), threading.Semaphore(1)]
+
+            def enc_stage(self, i, j):        # step i of the run, j-th step of this lane
+                src = hin[i % nh]
+                if B == 1:
+                    self.ctx_e._chk(L.jpezyb200_encode(self.ctx_e.h, src[0].data_ptr(), src[1].data_ptr(), src[2].data_ptr(), W, H, int(gray),
+                                                       self.hscan2[j & 1].data_ptr(), self.hscan2[j & 1].numel(), C.byref(self.nb2[j & 1]),
+                                                       C.byref(self.nbits)))
+                else:
+                    self.ctx_e.encode_batch(src[0], src[1], src[2], W, H, B, gray, self.hscan2[j & 1], hslot, self.hnb2[j & 1])
+
+            def dec_stage(self, j):
+                if B == 1:
+                    self.ctx_d._chk(L.jpezyb200_decode(self.ctx_d.h, self.hscan2[j & 1].data_ptr(), self.nb2[j & 1].value, C.byref(frame),
+                                                       int(gray), self.hout[0].data_ptr(), self.hout[1].data_ptr(), self.hout[2].data_ptr(),
+                                                       plane_len))
+                else:
+                    self.ctx_d.decode_batch(self.hscan2[j & 1], hslot, self.hnb2[j & 1], B, frame, gray, self.hout[0], self.hout[1],
+                                            self.hout[2], plane_len, self.hst)
+                    assert not self.hst.any()
+
+        lanes = [Lane(k) for k in range(n_lanes)]
         errs = []
 
-        def dec_worker():
+        def steps_of(lane):
+            return list(range(lane.k, n_pipe, n_lanes))
+
+        def dec_worker(lane):
             try:
                 torch.cuda.set_device(local_rank)
-                for i in range(n_pipe):
-                    filled[i & 1].acquire()
+                for j, _ in enumerate(steps_of(lane)):
+                    lane.filled[j & 1].acquire()
                     if errs:
                         return
-                    dec_stage(i)
-                    free[i & 1].release()
+                    lane.dec_stage(j)
+                    lane.free[j & 1].release()
             except Exception as ex:      # noqa: BLE001
                 errs.append(ex)
-                for sem in free:
+                for sem in lane.free:
                     sem.release()
 
-        enc_stage(0), dec_stage(0)       # warm the second context
+        def enc_worker(lane):
+            try:
+                torch.cuda.set_device(local_rank)
+                for j, i in enumerate(steps_of(lane)):
+                    lane.free[j & 1].acquire()
+                    if errs:
+                        break
+                    lane.enc_stage(i, j)
+                    lane.filled[j & 1].release()
+            except Exception as ex:      # noqa: BLE001
+                errs.append(ex)
+                for sem in lane.filled:
+                    sem.release()
+
+        for lane in lanes:               # warm every context
+            lane.enc_stage(0, 0), lane.dec_stage(0)
         barrier()
-        th = threading.Thread(target=dec_worker)
+        ths = [threading.Thread(target=dec_worker, args=(lane,)) for lane in lanes] + \
+              [threading.Thread(target=enc_worker, args=(lane,)) for lane in lanes[1:]]
         t0 = time.perf_counter()
-        th.start()
-        try:
-            for i in range(n_pipe):
-                free[i & 1].acquire()
-                if errs:
-                    break
-                enc_stage(i)
-                filled[i & 1].release()
-        except Exception as ex:      # noqa: BLE001
-            errs.append(ex)
-            for sem in filled:
-                sem.release()
-        th.join()
+        for th in ths:
+            th.start()
+        enc_worker(lanes[0])
+        for th in ths:
+            th.join()
         torch.cuda.synchronize()
         dt_pipe = time.perf_counter() - t0
         if errs:
             raise errs[0]
-        ctx2.close()
+        for lane in lanes:
+            lane.ctx_d.close()
+            if lane.k:
+                lane.ctx_e.close()
         dts = [dt_seq, dt_pipe]
         if dist is not None:
             t = torch.tensor(dts, device="cuda", dtype=torch.float64)
@@ -859,8 +888,9 @@ def main():
         v_pipe = world * B * npx * n_pipe / dts[1] / 1e6
         e2e = {"value": v_pipe, "unit": "MPix/s", "h2d_bytes_per_step": int(3 * npx * B + sb),
                "d2h_bytes_per_step": int(sb + 3 * plane_len * B), "steps": n_pipe,
-               "api": api + "; two-stage host pipeline: step i+1 is encoded (context 1, host thread 1) while step i is decoded "
-                            "(context 2, host thread 2), every step with its own H2D and D2H copies",
+               "api": api + "; two-stage host pipeline: step i+1 is encoded (one context and host thread) while step i is decoded "
+                            "(a second context and host thread), every step with its own H2D and D2H copies; %d such pipelines "
+                            "side by side (--e2e-lanes)" % n_lanes, "lanes": n_lanes,
                "one_call_after_the_other": {"value": v_seq, "unit": "MPix/s", "steps": n_e2e}}
         # The ceiling of this figure on this host: the step's copies alone (its host-to-device bytes and its device-to-host
         # bytes, pinned, in opposite directions at the same time on two streams, no kernels), all ranks at once.  A step can
