@@ -63,7 +63,9 @@ enum {
                                      (call site src/encoder/jpezy_writer.hpp:101-105). */
     JPEZYB200_OPT_TRANSFORM = 2,  /* forward/inverse transform kernel variant: 0 = fast path with
                                      guard band + exact recompute (default), 1 = FP64 separable
-                                     (validation build)                                           */
+                                     (validation build); A/B runs: 2 = one thread per block in the forward
+                                     kernel + first-generation inverse kernel, 3 = second-generation
+                                     (persistent, bulk-copy fed) forward kernel; same results        */
     JPEZYB200_OPT_BATCH_GROUP_BYTES = 4, /* jpezyb200_encode_batch / decode_batch: host<->device bytes per pipeline stage
                                      (default 96 MiB; images per group = value / (3 * pixels), at least 1)      */
     JPEZYB200_OPT_SHARD_SCRATCH_BYTES = 5, /* jpezyb200_shard_encode_*: bytes of device scratch for this rank's un-stuffed bits;

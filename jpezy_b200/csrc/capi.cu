@@ -324,8 +324,10 @@ static int launch_fwd_kernel(jpezyb200_ctx* ctx, const FwdParams& p, uint32_t ni
     if (ctx->transform_variant == 1) {
         dim3 grid((p.HU + kMcuPerCta - 1) / kMcuPerCta, p.VU, nimg);
         k_fwd_transform_f64<<<grid, kFwdThreads, 0, st>>>(p);
-    } else if (ctx->transform_variant == 0 && fwd2_ok(p)) {
-        // second-generation kernel: persistent CTAs, rows fetched by bulk copies (needs 16-byte aligned rows and buffers)
+    } else if (ctx->transform_variant == 3 && fwd2_ok(p)) {
+        // second-generation kernel: persistent CTAs, rows fetched by bulk copies (needs 16-byte aligned rows and buffers).  Measured
+        // against the production kernel below in one run: equal on a single 4K frame (28.3 us), 10 % slower on batches
+        // (404 against 365 us for 64 HD frames), half as fast on S-noise -- so it stays an A/B variant (JPEZYB200_OPT_TRANSFORM = 3)
         // JPEZY_B200_FWD_CFG (tuning runs): 83 = the compute warps store their own blocks (default), 82 = the DMA warp stores whole tiles,
         // 84 = as 83 with four input stages
         static const int cfg = [] { const char* e = std::getenv("JPEZY_B200_FWD_CFG"); return e ? std::atoi(e) : 83; }();

@@ -47,6 +47,24 @@ def test_coefficients_bit_exact(ctx, oracle, W, H, family, gray):
         bad[:5].tolist(), want[tuple(bad[:5].T)].tolist(), got[tuple(bad[:5].T)].tolist())
 
 
+@pytest.mark.parametrize("W,H", [(64, 48), (208, 128), (512, 512), (1920, 16), (4080, 48), (1024, 272)])
+@pytest.mark.parametrize("family", [0, 1, 2])
+@pytest.mark.parametrize("gray", [False, True])
+def test_second_generation_forward_kernel_bit_exact(ctx, oracle, W, H, family, gray):
+    """JPEZYB200_OPT_TRANSFORM = 3: the persistent, bulk-copy fed forward kernel (enc_transform2.cuh; rows must be 16-byte aligned).
+    An A/B variant since it lost to the production kernel on batches -- and held to the same bar."""
+    r, g, b = planes(family, W, H)
+    want = oracle.coefs(r, g, b, W, H, gray=gray)
+    ctx.set_option(capi.OPT_TRANSFORM, 3)
+    try:
+        got = gpu_coefs(ctx, r, g, b, W, H, gray=gray)[0]
+        scan, _ = ctx.encode(r, g, b, W, H, gray=gray)
+    finally:
+        ctx.set_option(capi.OPT_TRANSFORM, 0)
+    assert (want == got).all(), "%d coefficients differ" % int((want != got).sum())
+    assert scan == oracle.encode(r, g, b, W, H, gray=gray, scan_only=True)
+
+
 def test_guard_path_is_exercised(ctx, oracle):
     # flat gray tiles: every DC sits on a multiple of its quantiser whenever 8p % 16 == 0 -> the reference's FP64
     # rounding decides (SURVEY.md 7, hard part 1: DC = 8p -+ 1 ulp); the DC path evaluates ((S*c)*c)/4 as the reference does
