@@ -93,6 +93,7 @@ int jpezyb200_ctx_create(int device, jpezyb200_ctx** out)
     jpezyb200_ctx* ctx = new (std::nothrow) jpezyb200_ctx();
     if (!ctx) return JPEZYB200_ENOMEM;
     ctx->device = device;
+    if (cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->num_sms < 1) ctx->num_sms = 148;
     if (const char* e = std::getenv("JPEZY_B200_SYNC_ROUNDS")) ctx->sync_rounds = std::atoi(e);      // (debugging: JPEZYB200_OPT_SYNC_ROUNDS of every new context)
     int rc = [&]() -> int {
         JZ_CUDA_TRY(ctx, cudaSetDevice(device));
@@ -443,7 +444,7 @@ static int launch_entropy(jpezyb200_ctx* ctx, const int16_t* d_coefs, uint32_t W
     (void)jz_launch(k_block_bits, dim3(p.ntile, nimg), dim3(kEntThreads), 0, st, p);
     (void)jz_launch(k_scan_tiles, dim3(nimg), dim3(1024), 0, st, p);
     // grid-stride helpers: enough CTAs to fill the machine, split evenly over the images
-    const uint32_t per_img = std::max<uint32_t>(1u, std::min<uint32_t>(p.nchunk, (148u * 8u + nimg - 1) / nimg));
+    const uint32_t per_img = std::max<uint32_t>(1u, std::min<uint32_t>(p.nchunk, (uint32_t(ctx->num_sms) * 8u + nimg - 1) / nimg));
     (void)jz_launch(k_zero_ustream, dim3(per_img, nimg), dim3(256), 0, st, p);
     (void)jz_launch(k_scatter, dim3(p.ntile, nimg), dim3(kEntThreads), 0, st, p);
     (void)jz_launch(k_ff_count, dim3(per_img, nimg), dim3(kStuffThreads), 0, st, p);
@@ -561,7 +562,7 @@ int jpezyb200_synth_dev(jpezyb200_ctx* ctx, uint8_t* d_r, uint8_t* d_g, uint8_t*
     if (!d_r || !d_g || !d_b) return ctx->fail(JPEZYB200_EINVAL, "null pointer");
     JZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t npx = size_t(W) * H;
-    const uint32_t gx = uint32_t(std::min<size_t>((npx + 255) / 256, 148 * 16));
+    const uint32_t gx = uint32_t(std::min<size_t>((npx + 255) / 256, size_t(ctx->num_sms) * 16));
     k_synth<<<dim3(gx, nimg), 256, 0, pick_stream(ctx, stream)>>>(d_r, d_g, d_b, W, H, first_frame, family, 0u);
     ++ctx->launches;
     JZ_CUDA_TRY(ctx, cudaGetLastError());
@@ -576,7 +577,7 @@ int jpezyb200_synth_rows_dev(jpezyb200_ctx* ctx, uint8_t* d_r, uint8_t* d_g, uin
     if (!d_r || !d_g || !d_b) return ctx->fail(JPEZYB200_EINVAL, "null pointer");
     JZ_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t npx = size_t(W) * nrows;
-    const uint32_t gx = uint32_t(std::min<size_t>((npx + 255) / 256, 148 * 16));
+    const uint32_t gx = uint32_t(std::min<size_t>((npx + 255) / 256, size_t(ctx->num_sms) * 16));
     k_synth<<<dim3(gx, 1), 256, 0, pick_stream(ctx, stream)>>>(d_r, d_g, d_b, W, nrows, frame, family, y0);
     ++ctx->launches;
     JZ_CUDA_TRY(ctx, cudaGetLastError());
