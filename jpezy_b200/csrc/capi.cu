@@ -13,6 +13,7 @@
 #include "dec_entropy.cuh"
 #include "dec_transform.cuh"
 #include "dec_transform2.cuh"
+#include "dec_transform_g.cuh"
 #include "enc_entropy.cuh"
 #include "enc_transform.cuh"
 #include "enc_transform2.cuh"
@@ -190,13 +191,15 @@ void jpezyb200_ctx_destroy(jpezyb200_ctx* ctx)
     jz_devbuf* bufs[] = {&ctx->coefs, &ctx->blk_off, &ctx->tile_sum, &ctx->tile_base, &ctx->img_bits, &ctx->ustream,
                          &ctx->ff_sum, &ctx->ff_base, &ctx->planes_in, &ctx->planes_out, &ctx->scan_io, &ctx->sizes_io,
                          &ctx->dec_scanbytes, &ctx->dec_chunk_cnt, &ctx->dec_chunk_base, &ctx->dec_ubytes, &ctx->dec_state,
-                         &ctx->dec_dirty, &ctx->dec_subblk, &ctx->dec_dc, &ctx->dec_dcd, &ctx->blk_meta, &ctx->dec_status, &ctx->dec_changed, &ctx->dec_flags, &ctx->shard_geom, &ctx->dec_mcnt, &ctx->dec_mbase, &ctx->dec_seg};
+                         &ctx->dec_dirty, &ctx->dec_subblk, &ctx->dec_dc, &ctx->dec_dcd, &ctx->blk_meta, &ctx->dec_status, &ctx->dec_changed, &ctx->dec_flags, &ctx->inv_samples, &ctx->shard_geom, &ctx->dec_mcnt, &ctx->dec_mbase, &ctx->dec_seg};
     for (jz_devbuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->d_enc_lut) cudaFree(ctx->d_enc_lut);
     if (ctx->d_dec_lut) cudaFree(ctx->d_dec_lut);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_y_exact) cudaFree(ctx->d_y_exact);
+    for (void* tb : ctx->invg_tab)
+        if (tb) cudaFree(tb);
     for (void* tb : ctx->inv2_tab)
         if (tb) cudaFree(tb);
     jz::batch_pipe_destroy(ctx);

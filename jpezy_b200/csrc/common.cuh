@@ -109,6 +109,11 @@ struct jpezyb200_ctx {
     void* inv2_tab[kInv2Slots] = {};
     uint16_t inv2_key[kInv2Slots][3][64] = {};
     int inv2_next = 0;
+    void* invg_tab[kInv2Slots] = {};           // ... and of k_idct_blocks (general frame layouts)
+    uint16_t invg_key[kInv2Slots][3][64] = {};
+    int invg_next = 0;
+    bool invg_attr_set = false;
+    jz_devbuf inv_samples;                     // [nimg][blocks][64] int16 between k_idct_blocks and k_colour_general
 
     // device-resident tables
     jz::HuffEncLut* d_enc_lut = nullptr;  // [2]
