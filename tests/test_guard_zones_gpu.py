@@ -72,3 +72,54 @@ def test_device_entry_points_stay_inside_their_buffers(ctx, W, H, family, gray, 
     for name, gbuf in [("planes_in", planes_in[0]), ("planes_in", planes_in[1]), ("planes_in", planes_in[2]), ("coefs", coefs), ("coefs2", coefs2),
                        ("scan", scan), ("nbytes", nbytes), ("nbits", nbits), ("status", status), ("out", out[0]), ("out", out[1]), ("out", out[2])]:
         assert gbuf.intact(), "guard zone around %s was written" % name
+
+
+LAYOUTS = {"444": ((1, 1, 1), (1, 1, 1)), "422": ((2, 1, 1), (1, 1, 1)), "440": ((1, 1, 1), (2, 1, 1)), "gray1": ((1,), (1,))}
+
+
+@pytest.mark.parametrize("layout", sorted(LAYOUTS))
+@pytest.mark.parametrize("W,H", [(70, 45), (129, 257), (640, 368), (8, 8)])
+@pytest.mark.parametrize("gray", [False, True])
+def test_general_layout_inverse_equals_validation_kernel_and_stays_inside(ctx, layout, W, H, gray):
+    """the fast inverse path of the sampling layouts jpezy's encoder never writes (dec_transform_g.cuh) against the FP64 validation
+    kernel (JPEZYB200_OPT_TRANSFORM = 1) on random coefficients -- small ones, DC-only blocks, full-range ones that drive the
+    samples far outside [0, 255] -- with guard zones around the planes."""
+    hs, vs = LAYOUTS[layout]
+    f = J.default_frame(W, H)
+    f.ncomp = len(hs)
+    for i in range(len(hs)):
+        f.hs[i], f.vs[i] = hs[i], vs[i]
+    if len(hs) == 3:
+        f.tq[2] = 1
+    hmax, vmax = max(hs), max(vs)
+    hu, vu = -(-W // (8 * hmax)), -(-H // (8 * vmax))
+    nb = sum(a * b for a, b in zip(hs, vs))
+    pl = capi.plane_bytes(f)
+    rng = np.random.default_rng(W * 1000 + H)
+    c = np.zeros((hu * vu * nb, 64), dtype=np.int16)
+    c[:, 0] = rng.integers(-100, 100, size=c.shape[0])
+    kind = rng.integers(0, 4, size=c.shape[0])
+    m = kind == 1
+    c[m, 1:6] = rng.integers(-4, 5, size=(int(m.sum()), 5))
+    m = kind == 2
+    c[m, :] = (rng.integers(-30, 31, size=(int(m.sum()), 64)) * (rng.random((int(m.sum()), 64)) < 0.3)).astype(np.int16)
+    m = kind == 3
+    c[m, :] = rng.integers(-1023, 1024, size=(int(m.sum()), 64)).astype(np.int16)
+    d = Guarded(c.size, torch.int16)
+    d.view.copy_(torch.from_numpy(c.reshape(-1)).cuda())
+    outs = []
+    for variant in (0, 1):
+        ctx.set_option(capi.OPT_TRANSFORM, variant)
+        try:
+            out = [Guarded(pl, torch.uint8, fill=0x33) for _ in range(3)]
+            ctx.transform_inv_dev(d.view, f, 1, gray, out[0].view, out[1].view, out[2].view, pl, stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+        finally:
+            ctx.set_option(capi.OPT_TRANSFORM, 0)
+        for o in out:
+            assert o.intact(), "guard zone around an output plane was written (variant %d)" % variant
+        outs.append([o.view.clone() for o in out])
+    assert d.intact()
+    for a, b in zip(*outs):
+        nd = int((a != b).sum())
+        assert nd == 0, "%d samples differ from the validation kernel" % nd
