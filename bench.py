@@ -537,6 +537,8 @@ def main():
     ap.add_argument("--shard", action="store_true", help="c4 under torchrun: ONE image split by MCU rows over the ranks (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=0, help="steps in flight in the device-timed loop: step i runs on context / stream i mod F "
+                    "(0 = 4 for one image per step, 2 for batches, which nearly fill the machine by themselves)")
     ap.add_argument("--e2e-lanes", type=int, default=2, help="host pipelines (encode thread + decode thread each) run side by side in the e2e measurement")
     ap.add_argument("--no-configs", action="store_true", help="skip the c3 / c5 / c4_shard measurements appended to the default line")
     ap.add_argument("--host-lengths", action="store_true", help="segment lengths through a host array between encoder and decoder (round-1 step)")
@@ -623,9 +625,20 @@ def main():
         h_nbytes[k] = h_nb[k]
         ctx.decode_batch_dev(enc_args[k][7], slot, h_nb[k], B, frame, gray, *dec_out[k], stream=sp)
 
-    def step_dev(k):
-        ctx.encode_batch_dev(*enc_args[k], stream=sp)
-        ctx.decode_batch_dev2(enc_args[k][7], slot, enc_args[k][9], bound[0], B, frame, gray, *dec_out[k], stream=sp)
+    # Steps are independent (every step has its own frame of the ring), and half of a single-frame step is latency bound (the chains
+    # of the entropy decoder occupy a fraction of the machine): F steps in flight -- step i on context / stream i mod F, as a
+    # server that transcodes a stream of frames would run them -- fill those holes.  F = 1 is one step after the other.
+    n_fly = args.in_flight if args.in_flight > 0 else (4 if B == 1 else 2)
+    if args.host_lengths:
+        n_fly = 1
+    n_fly = max(1, min(n_fly, ring))
+    fly_ctx = [ctx] + [J.Context(local_rank) for _ in range(n_fly - 1)]
+    fly_stream = [stream] + [torch.cuda.Stream() for _ in range(n_fly - 1)]
+    fly_sp = [x.cuda_stream for x in fly_stream]
+
+    def step_dev(k, j=0):
+        fly_ctx[j].encode_batch_dev(*enc_args[k], stream=fly_sp[j])
+        fly_ctx[j].decode_batch_dev2(enc_args[k][7], slot, enc_args[k][9], bound[0], B, frame, gray, *dec_out[k], stream=fly_sp[j])
 
     for k in range(ring):
         step_host(k)
@@ -641,6 +654,34 @@ def main():
     for i in range(max(args.warmup, ring)):      # every ring slot is produced at least once before timing
         step(i % ring)
     barrier()
+
+    def timed_steps(nf):
+        """K steps, nf in flight: device time between an event in front of the first and one behind the last step of every stream"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for j in range(1, nf):
+            fly_stream[j].wait_event(e0)
+        for i in range(args.steps):
+            if nf == 1:
+                step(i % ring)
+            else:
+                step_dev(i % ring, i % nf)
+        for j in range(1, nf):
+            ev = torch.cuda.Event()
+            ev.record(fly_stream[j])
+            stream.wait_event(ev)
+        e1.record(stream)
+        barrier()
+        t_ms = e0.elapsed_time(e1)
+        if dist is not None:
+            tt = torch.tensor([t_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_ms = float(tt.item())
+        return t_ms
+    if n_fly > 1:
+        for i in range(max(args.warmup, 2 * n_fly)):
+            step_dev(i % ring, i % n_fly)
+        barrier()
     def check_round_trip(slot_k):
         """status of every decode of the ring, segment sizes, and the PSNR of one decoded frame against its input (parity itself
         is the tests' job; this catches a step that does no work, or a segment that outgrew the bound of the device-length form)"""
@@ -662,21 +703,15 @@ def main():
     d_out.zero_()          # the timed loop has to produce the pictures again
 
     sampler.mark = True
-    l0 = ctx.stat(capi.STAT_KERNEL_LAUNCHES)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.steps):
-        step(i % ring)
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.stat(capi.STAT_KERNEL_LAUNCHES) - l0
+    l0 = sum(c.stat(capi.STAT_KERNEL_LAUNCHES) for c in fly_ctx)
+    ms = timed_steps(n_fly)
+    launches = sum(c.stat(capi.STAT_KERNEL_LAUNCHES) for c in fly_ctx) - l0
     psnr_after = check_round_trip((args.steps - 1) % ring)      # the last step's output, after the timed loop
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     value = world * B * npx * args.steps / (ms * 1e-3) / 1e6
+    one_in_flight = None
+    if n_fly > 1:      # the same K steps one after the other on one stream, for comparison
+        ms1 = timed_steps(1)
+        one_in_flight = {"value": world * B * npx * args.steps / (ms1 * 1e-3) / 1e6, "unit": "MPix/s", "ms_per_step": ms1 / args.steps}
 
     # ---- per-stage device times + roofline of the dominant kernel (forward transform), same ring ----
     nm = capi.num_mcus(W, H)
@@ -966,7 +1001,10 @@ def main():
                            "family": "S-photo" if args.family == 0 else "S-noise",
                            "l2": "ring of %d distinct input/output frame sets (%.0f MB) rotated between steps; > 126 MB L2" % (
                                ring, ring * (in_bytes + out_bytes) / 1e6),
-                           "sharding": "by image, no data-path collective"},
+                           "sharding": "by image, no data-path collective",
+                           "steps_in_flight": "%d (step i runs on context / stream i mod %d; device time from an event in front of the first "
+                                              "to one behind the last step of every stream)" % (n_fly, n_fly) if n_fly > 1 else "1 (one step after the other on one stream)"},
+                "steps_in_flight": n_fly, "one_step_in_flight": one_in_flight,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "stages": stages, "configs": configs, "roundtrip_psnr_db": psnr, "roundtrip_psnr_db_after_timed_loop": psnr_after,
                 "segment_lengths": "host array (read back between encoder and decoder)" if args.host_lengths else "device memory (jpezyb200_decode_batch_dev2, sized for %d bytes per segment)" % bound[0]}
