@@ -71,6 +71,10 @@ enum {
     JPEZYB200_OPT_SHARD_SCRATCH_BYTES = 5, /* jpezyb200_shard_encode_*: bytes of device scratch for this rank's un-stuffed bits;
                                      0 (default) = the reference's own bound, 3 bytes per pixel of the shard.  A shard that does
                                      not fit makes EVERY rank report overflow in phase D (no silently short segment) */
+    JPEZYB200_OPT_SYNC_GUESSES = 6, /* decoder, first self-synchronisation launch: 0 (default) = one guessed state per subsequence;
+                                     1 = on inputs too small to fill the device (a single frame) one chain per block position of
+                                     the MCU, all at once: shortest latency of ONE decode (a 1080p frame: -11 %), six times the
+                                     work -- with several decodes in flight on other contexts the default is faster */
     JPEZYB200_OPT_SYNC_ROUNDS = 3 /* self-synchronisation launches enqueued after the first one by the
                                      decoder: n > 0 = exactly n, no host round trip (default 3; the first launch checks
                                      the boundaries of its thread blocks itself, so on ordinary streams none of them has work and

@@ -95,7 +95,8 @@ int jpezyb200_ctx_create(int device, jpezyb200_ctx** out)
     if (!ctx) return JPEZYB200_ENOMEM;
     ctx->device = device;
     if (cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->num_sms < 1) ctx->num_sms = 148;
-    if (const char* e = std::getenv("JPEZY_B200_SYNC_ROUNDS")) ctx->sync_rounds = std::atoi(e);      // (debugging: JPEZYB200_OPT_SYNC_ROUNDS of every new context)
+    if (const char* e = std::getenv("JPEZY_B200_SYNC_ROUNDS")) ctx->sync_rounds = std::atoi(e);
+    if (const char* e = std::getenv("JPEZY_B200_DEC_HYP")) ctx->sync_guesses = std::max(0, std::min(2, std::atoi(e)));      // (JPEZYB200_OPT_SYNC_GUESSES of every new context)      // (debugging: JPEZYB200_OPT_SYNC_ROUNDS of every new context)
     int rc = [&]() -> int {
         JZ_CUDA_TRY(ctx, cudaSetDevice(device));
         JZ_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -227,6 +228,10 @@ int jpezyb200_set_option(jpezyb200_ctx* ctx, int option, int64_t value)
     case JPEZYB200_OPT_SHARD_SCRATCH_BYTES:
         if (value < 0) return ctx->fail(JPEZYB200_EINVAL, "scratch bytes must be >= 0");
         ctx->shard_scratch = value;
+        return JPEZYB200_OK;
+    case JPEZYB200_OPT_SYNC_GUESSES:
+        if (value < 0 || value > 2) return ctx->fail(JPEZYB200_EINVAL, "sync guesses: 0 (one per subsequence), 1 (one per block position on latency-bound inputs), 2 (always)");
+        ctx->sync_guesses = int(value);
         return JPEZYB200_OK;
     case JPEZYB200_OPT_SYNC_ROUNDS:
         if (value < 0 || value > 64) return ctx->fail(JPEZYB200_EINVAL, "sync rounds must be in 0..64");

@@ -99,6 +99,7 @@ struct jpezyb200_ctx {
     std::string err;
     int pad_ones = 1;
     int transform_variant = 0;
+    int sync_guesses = 0;     // JPEZYB200_OPT_SYNC_GUESSES
     int sync_rounds = 3;      // launches behind launch 0 (which checks the CTA boundaries itself): two that repair, one that verifies
     int64_t shard_scratch = 0;                 // JPEZYB200_OPT_SHARD_SCRATCH_BYTES (0 = 3 bytes per pixel)
     int64_t group_bytes = int64_t(96) << 20;   // host<->device bytes per stage of the pipelined host batches

@@ -50,6 +50,34 @@ def test_entropy_decode_matches_sequential_decoder(ctx, oracle, W, H, family):
     assert (got[0] == want).all()
 
 
+@pytest.mark.parametrize("W,H", SIZES + [(1024, 512), (1920, 1088)])
+@pytest.mark.parametrize("family", [0, 1, 2])
+@pytest.mark.parametrize("gray", [False, True])
+def test_one_chain_per_guess_matches_sequential_decoder(ctx, oracle, W, H, family, gray):
+    """JPEZYB200_OPT_SYNC_GUESSES = 1: the first synchronisation launch runs one chain per block position of the MCU
+    (k_sync_decode_hyp) on inputs that cannot fill the device -- the latency form; same coefficients, same status.  --gray S-noise
+    is the stream that stays unsynchronised for whole CTAs (the follow-up launches repair it)."""
+    r, g, b = planes(family, W, H)
+    f = oracle.encode(r, g, b, W, H, gray=gray)
+    want = oracle.decode_coefs(f)
+    ctx.set_option(capi.OPT_SYNC_GUESSES, 1)
+    try:
+        got, st = gpu_entropy_decode(ctx, [split(f), split(f)], W, H)
+    finally:
+        ctx.set_option(capi.OPT_SYNC_GUESSES, 0)
+    assert st[0] in (0, capi.EAGAIN) and st[1] == st[0]
+    if st[0] == capi.EAGAIN:           # legitimate on the device-resident entry point: the host entry point decodes again
+        ctx.set_option(capi.OPT_SYNC_GUESSES, 1)
+        try:
+            R, G, B = ctx.decode(split(f), J.default_frame(W, H))
+        finally:
+            ctx.set_option(capi.OPT_SYNC_GUESSES, 0)
+        _, _, R0, G0, B0 = oracle.decode(f)
+        assert (R == R0).all() and (G == G0).all() and (B == B0).all()
+    else:
+        assert (got[0] == want).all() and (got[1] == want).all()
+
+
 def test_entropy_decode_with_trailing_eoi_and_batch(ctx, oracle):
     W, H = 136, 72
     files = [oracle.encode(*planes(fam, W, H, frame=k), W, H) for k, fam in enumerate([0, 1, 2, 1, 0])]

@@ -55,6 +55,22 @@ def test_full_size_second_generation_forward_kernel(ctx, oracle, family):
     assert hashlib.sha256(scan).hexdigest() == hashlib.sha256(oracle.encode(r, g, b, W, H, scan_only=True)).hexdigest()
 
 
+@pytest.mark.parametrize("family", [0, 1])
+def test_full_size_one_chain_per_guess(ctx, oracle, family):
+    # the latency form of the first synchronisation launch (JPEZYB200_OPT_SYNC_GUESSES = 1) on a whole 4K frame
+    W, H = 3840, 2160
+    d = synth_dev(ctx, W, H, family=family)
+    r, g, b = (d[c].cpu().numpy() for c in range(3))
+    want = oracle.encode(r, g, b, W, H)
+    ctx.set_option(capi.OPT_SYNC_GUESSES, 1)
+    try:
+        R, G, B = ctx.decode(want[644:-2], J.default_frame(W, H))
+    finally:
+        ctx.set_option(capi.OPT_SYNC_GUESSES, 0)
+    _, _, R0, G0, B0 = oracle.decode(want)
+    assert int((R != R0).sum()) + int((G != G0).sum()) + int((B != B0).sum()) == 0
+
+
 def test_c5_shape_properties(ctx):
     W, H = 32768, 1024                                   # a band of the 32768 x 32768 image: 2048 x 64 MCUs
     d = synth_dev(ctx, W, H)

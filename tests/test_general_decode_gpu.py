@@ -74,6 +74,21 @@ def test_general_baseline_decode_matches_reference_decoder(tmp_path, oracle, nam
         assert q.returncode == 0 and (tmp_path / "ref.ppm").read_text() == out.read_text()
 
 
+@pytest.mark.parametrize("name,mode,kw", [c for c in CASES if c[0] in ("444", "422", "420_q95", "gray")], ids=["444", "422", "420_q95", "gray"])
+def test_general_baseline_decode_one_chain_per_guess(tmp_path, oracle, name, mode, kw):
+    """the multi-guess first synchronisation launch (JPEZY_B200_DEC_HYP=1 = JPEZYB200_OPT_SYNC_GUESSES of every new context) on
+    MCUs of 3, 4 and 6 blocks (one block: it falls back to the single guess)"""
+    W, H = 640, 360
+    f = jpeg_bytes(picture(W, H, 11), mode, **kw)
+    jpg, out = tmp_path / "in.jpg", tmp_path / "out.ppm"
+    jpg.write_bytes(f)
+    Wd, Hd, R0, G0, B0 = oracle.decode(f)
+    p = subprocess.run([DEC, str(jpg), str(out)], capture_output=True, text=True, env=dict(os.environ, JPEZY_B200_DEC_HYP="1"))
+    assert p.returncode == 0, p.stderr
+    vals = np.array(" ".join(out.read_text().split("\n")[4:]).split(), dtype=np.int64).reshape(-1, 3)
+    assert (vals[:, 0] == R0[: W * H]).all() and (vals[:, 1] == G0[: W * H]).all() and (vals[:, 2] == B0[: W * H]).all()
+
+
 def test_decode_again_when_the_enqueued_synchronisation_launches_were_not_enough(tmp_path, oracle):
     """a high-quality file needs more self-synchronisation launches than a context that enqueues a single one provides: the device
     reports JPEZYB200_EAGAIN and jpezyb200_decode decodes again with the host-polled loop.  (The writing pass of the first attempt

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--gray", action="store_true")
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--variant", type=int, default=0, help="JPEZYB200_OPT_TRANSFORM")
+    ap.add_argument("--guesses", type=int, default=0, help="JPEZYB200_OPT_SYNC_GUESSES")
     ap.add_argument("--lib", default="", help="A/B runs: another build of libjpezy_b200.so to load instead of the in-tree one")
     a = ap.parse_args()
     import numpy as np
@@ -34,6 +35,8 @@ def main():
     ctx = J.Context(0)
     if a.variant:
         ctx.set_option(capi.OPT_TRANSFORM, a.variant)
+    if a.guesses:
+        ctx.set_option(capi.OPT_SYNC_GUESSES, a.guesses)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
